@@ -1,0 +1,132 @@
+// common.cuh -- shared host/device plumbing for libnuk (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <string.h>
+#include <type_traits>
+#include "../../include/nuk.h"
+
+#define NUK_API extern "C" __attribute__((visibility("default")))
+#define NUK_HD __host__ __device__ __forceinline__
+#define NUK_D __device__ __forceinline__
+
+namespace nuk {
+
+// ------------------------------------------------------------------ errors
+void set_error(int status, const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+#define NUK_CUDA(expr)                                                    \
+  do {                                                                    \
+    cudaError_t _e = (expr);                                              \
+    if (_e != cudaSuccess) return nuk::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+  } while (0)
+#define NUK_TRY(expr)            \
+  do {                           \
+    int _s = (expr);             \
+    if (_s != NUK_OK) return _s; \
+  } while (0)
+
+// ------------------------------------------------------------------ runtime state
+struct DeviceInfo {
+  int device;
+  int sm_count;
+  size_t l2_bytes;
+};
+const DeviceInfo *device_info();      // current device of this thread (lazy init); nullptr + error if none
+cudaStream_t current_stream();        // thread-local stream used by BMAS_* symbols
+void count_launch(unsigned n = 1);    // gpu_launches bookkeeping
+long option(const char *name);        // NUK_* knobs
+int post_launch(const char *kernel);  // cudaGetLastError -> status
+
+// scratch memory private to (thread, stream): reduction partials etc.
+int scratch(cudaStream_t s, size_t bytes, void **dptr);
+// pinned result slot private to the thread (8 * 64 bytes)
+int pinned_slot(void **hptr);
+
+// grid size for a persistent / grid-stride kernel: min(work_blocks, sm_count * mult)
+int grid_for(size_t work_blocks, int blocks_per_sm);
+
+// ------------------------------------------------------------------ dtype traits
+template <int DT> struct CType;
+template <> struct CType<NUK_F32> { using type = float; };
+template <> struct CType<NUK_F64> { using type = double; };
+template <> struct CType<NUK_I64> { using type = int64_t; };
+template <> struct CType<NUK_I32> { using type = int32_t; };
+template <> struct CType<NUK_I16> { using type = int16_t; };
+template <> struct CType<NUK_I8> { using type = int8_t; };
+template <> struct CType<NUK_U64> { using type = uint64_t; };
+template <> struct CType<NUK_U32> { using type = uint32_t; };
+template <> struct CType<NUK_U16> { using type = uint16_t; };
+template <> struct CType<NUK_U8> { using type = uint8_t; };
+
+inline size_t dtype_size(int dt) {
+  switch (dt) {
+    case NUK_F32: case NUK_I32: case NUK_U32: return 4;
+    case NUK_F64: case NUK_I64: case NUK_U64: return 8;
+    case NUK_I16: case NUK_U16: return 2;
+    case NUK_I8: case NUK_U8: return 1;
+    default: return 0;
+  }
+}
+
+// a scalar operand travelling by value in the kernel parameters
+union Scalar64 {
+  double d; float f; int64_t i64; uint64_t u64; int32_t i32; uint32_t u32;
+  int16_t i16; uint16_t u16; int8_t i8; uint8_t u8; unsigned char bytes[8];
+};
+template <typename T> NUK_HD T scalar_as(const Scalar64 &s) {
+  T v;
+  memcpy(&v, s.bytes, sizeof(T));
+  return v;
+}
+
+// ------------------------------------------------------------------ vector packs
+constexpr int kThreads = 256;
+
+template <typename T, int N> struct alignas(sizeof(T) * N) Pack { T v[N]; };
+
+// streaming (evict-first) 2/4/8/16-byte global accesses. Plain ld.global/st.global with the
+// .cs policy: legal when OUT aliases an input (the non-coherent .nc path is not).
+template <int BYTES> struct RawVec;
+template <> struct RawVec<1> { using type = unsigned char; };
+template <> struct RawVec<2> { using type = unsigned short; };
+template <> struct RawVec<4> { using type = unsigned int; };
+template <> struct RawVec<8> { using type = uint2; };
+template <> struct RawVec<16> { using type = uint4; };
+
+template <typename P> NUK_D P ld_stream(const P *p) {
+  using R = typename RawVec<sizeof(P)>::type;
+  R r = __ldcs(reinterpret_cast<const R *>(p));
+  P out;
+  memcpy(&out, &r, sizeof(P));
+  return out;
+}
+template <typename P> NUK_D void st_stream(P *p, const P &v) {
+  using R = typename RawVec<sizeof(P)>::type;
+  R r;
+  memcpy(&r, &v, sizeof(P));
+  __stcs(reinterpret_cast<R *>(p), r);
+}
+template <typename P> NUK_D P ld_keep(const P *p) {  // default policy (operand is re-read: keep in L1/L2)
+  using R = typename RawVec<sizeof(P)>::type;
+  R r = *reinterpret_cast<const R *>(p);
+  P out;
+  memcpy(&out, &r, sizeof(P));
+  return out;
+}
+
+inline bool aligned_to(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+
+// ------------------------------------------------------------------ nd descriptor (device side)
+struct NdDesc {
+  int rank;                       // <= NUK_MAX_RANK, after coalescing
+  int64_t dims[NUK_MAX_RANK];
+  int64_t stride[3][NUK_MAX_RANK];  // operand 0 = out, 1 = x, 2 = y (elements)
+};
+
+// host side: normalise (dims, strides of nops operands) -> compact descriptor.
+// strides layout: strides[op * NUK_MAX_RANK + axis]
+int coalesce(int nops, int rank, int64_t *dims, int64_t *strides);
+
+}  // namespace nuk

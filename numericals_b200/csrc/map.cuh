@@ -1,0 +1,381 @@
+// map.cuh -- the three elementwise kernels of libnuk and their launcher.
+//
+//   k_map_flat : everything contiguous (or scalar).  Persistent grid-stride over tiles of
+//                kThreads*UNROLL packs; one pack = 16 bytes of the widest operand type,
+//                all loads of a tile issued before the first use (UNROLL independent
+//                128-bit requests per operand per thread in flight), streaming stores.
+//   k_map_rows : inner axis contiguous for OUT, inputs contiguous or broadcast (stride 0)
+//                along it; outer axes arbitrary.  A CTA owns a column tile x a group of
+//                consecutive rows; an operand that does not vary with the row (row-vector
+//                broadcast) is staged ONCE in registers, a column-vector operand is one
+//                broadcast load per row.  This replaces the reference's one-C-call-per-row
+//                loop (src/utils/ptr-iterate-but-inner.lisp:35-64).
+//   k_map_nd   : any strides (0 / negative / transposed), rank <= 8: per-element index
+//                decomposition (no division when rank == 1, which is the BMAS strided call).
+//
+// A functor F provides: In (input element type), Out, kArity (1|2) and
+//   __device__ Out operator()(In a [, In b]).
+// OUT may alias X and/or Y exactly: every thread reads the elements it is going to
+// overwrite before it writes them, and no thread reads another thread's elements.
+#pragma once
+#include "common.cuh"
+
+namespace nuk {
+
+template <typename T> struct Operand {
+  const T *ptr;   // nullptr => scalar by value
+  Scalar64 val;
+};
+
+template <class F> struct PackOf {
+  using In = typename F::In;
+  using Out = typename F::Out;
+  static constexpr int kWide = sizeof(In) > sizeof(Out) ? sizeof(In) : sizeof(Out);
+  static constexpr int E = 16 / kWide;  // elements per pack
+  using PIn = Pack<In, E>;
+  using POut = Pack<Out, E>;
+};
+
+template <class F> NUK_D typename F::Out apply(const F &f, typename F::In a, typename F::In b) {
+  if constexpr (F::kArity == 2) return f(a, b);
+  else return f(a);
+}
+
+// ------------------------------------------------------------------ flat kernel
+template <class F, int UNROLL>
+__global__ void __launch_bounds__(kThreads)
+k_map_flat(size_t n, const typename F::In *x, const typename F::In *y, typename F::Out *out,
+           int x_scalar, int y_scalar, Scalar64 xv, Scalar64 yv, F f) {
+  using In = typename F::In;
+  using Out = typename F::Out;
+  using P = PackOf<F>;
+  constexpr int E = P::E;
+  using PIn = typename P::PIn;
+  using POut = typename P::POut;
+
+  In xs = In(), ys = In();
+  if (x_scalar) xs = x ? x[0] : scalar_as<In>(xv);
+  if (F::kArity == 2 && y_scalar) ys = y ? y[0] : scalar_as<In>(yv);
+
+  const size_t npack = n / E;
+  constexpr size_t kTile = (size_t)kThreads * UNROLL;
+  const size_t nfull = npack / kTile;
+  const PIn *xp = reinterpret_cast<const PIn *>(x);
+  const PIn *yp = reinterpret_cast<const PIn *>(y);
+  POut *op = reinterpret_cast<POut *>(out);
+
+  for (size_t t = blockIdx.x; t < nfull; t += gridDim.x) {
+    const size_t base = t * kTile + threadIdx.x;
+    PIn a[UNROLL], b[UNROLL];
+    if (!x_scalar) {
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) a[u] = ld_stream(xp + base + (size_t)u * kThreads);
+    }
+    if (F::kArity == 2 && !y_scalar) {
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) b[u] = ld_stream(yp + base + (size_t)u * kThreads);
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      POut r;
+#pragma unroll
+      for (int e = 0; e < E; ++e)
+        r.v[e] = apply(f, x_scalar ? xs : a[u].v[e], (F::kArity == 2 && !y_scalar) ? b[u].v[e] : ys);
+      st_stream(op + base + (size_t)u * kThreads, r);
+    }
+  }
+  // remainder packs and the element tail: one CTA (the one whose turn it would be)
+  if (blockIdx.x == nfull % gridDim.x) {
+    for (size_t p = nfull * kTile + threadIdx.x; p < npack; p += kThreads) {
+      PIn a, b;
+      if (!x_scalar) a = ld_stream(xp + p);
+      if (F::kArity == 2 && !y_scalar) b = ld_stream(yp + p);
+      POut r;
+#pragma unroll
+      for (int e = 0; e < E; ++e)
+        r.v[e] = apply(f, x_scalar ? xs : a.v[e], (F::kArity == 2 && !y_scalar) ? b.v[e] : ys);
+      st_stream(op + p, r);
+    }
+    const size_t i = npack * E + threadIdx.x;
+    if (i < n) {
+      const In a = x_scalar ? xs : x[i];
+      const In b = (F::kArity == 2 && !y_scalar) ? y[i] : ys;
+      out[i] = apply(f, a, b);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ rows kernel
+struct RowsDesc {
+  int64_t ncols;                 // inner (contiguous) extent
+  int64_t nrows;                 // extent of the last outer axis (rows a CTA may group)
+  int64_t row_stride[3];         // out, x, y stride of that axis (elements)
+  int col_stride[3];             // 1 or 0 for x, y along the inner axis (out is always 1)
+  int nouter;                    // remaining outer axes (rank - 2), slowest first
+  int64_t odims[NUK_MAX_RANK];
+  int64_t ostride[3][NUK_MAX_RANK];
+  int rows_per_cta;
+};
+
+template <class F, int UNROLL>
+__global__ void __launch_bounds__(kThreads)
+k_map_rows(RowsDesc d, const typename F::In *x, const typename F::In *y, typename F::Out *out,
+           Scalar64 xv, Scalar64 yv, F f) {
+  using In = typename F::In;
+  using Out = typename F::Out;
+  using P = PackOf<F>;
+  constexpr int E = P::E;
+  using PIn = typename P::PIn;
+  using POut = typename P::POut;
+
+  // blockIdx.y -> column tile; blockIdx.x -> (outer index, row group)
+  const int64_t row_groups = (d.nrows + d.rows_per_cta - 1) / d.rows_per_cta;
+  int64_t g = blockIdx.x;
+  const int64_t rg = g % row_groups;
+  g /= row_groups;
+  int64_t off_o = 0, off_x = 0, off_y = 0;
+  for (int a = d.nouter - 1; a >= 0; --a) {
+    const int64_t i = g % d.odims[a];
+    g /= d.odims[a];
+    off_o += i * d.ostride[0][a];
+    off_x += i * d.ostride[1][a];
+    off_y += i * d.ostride[2][a];
+  }
+  const int64_t r0 = rg * d.rows_per_cta;
+  const int64_t r1 = (r0 + d.rows_per_cta < d.nrows) ? r0 + d.rows_per_cta : d.nrows;
+
+  const int64_t c0 = ((int64_t)blockIdx.y * kThreads * UNROLL + threadIdx.x) * E;  // first column of pack u=0
+  const bool x_rowinv = (d.row_stride[1] == 0), y_rowinv = (d.row_stride[2] == 0);
+  const bool x_col = d.col_stride[1] != 0, y_col = (F::kArity == 2) && d.col_stride[2] != 0;
+
+  const In *xb = x ? x + off_x : nullptr;
+  const In *yb = y ? y + off_y : nullptr;
+  Out *ob = out + off_o;
+
+  // packs fully inside the row use the vector path; the ragged right edge goes scalar
+  bool full[UNROLL];
+#pragma unroll
+  for (int u = 0; u < UNROLL; ++u) full[u] = c0 + (int64_t)u * kThreads * E + E <= d.ncols;
+
+  PIn ha[UNROLL], hb[UNROLL];  // hoisted row-invariant operands
+  if (x_col && x_rowinv) {
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u)
+      if (full[u]) ha[u] = ld_keep(reinterpret_cast<const PIn *>(xb + c0 + (int64_t)u * kThreads * E));
+  }
+  if (y_col && y_rowinv) {
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u)
+      if (full[u]) hb[u] = ld_keep(reinterpret_cast<const PIn *>(yb + c0 + (int64_t)u * kThreads * E));
+  }
+
+  for (int64_t r = r0; r < r1; ++r) {
+    const In *xr = xb ? xb + r * d.row_stride[1] : nullptr;
+    const In *yr = yb ? yb + r * d.row_stride[2] : nullptr;
+    Out *orow = ob + r * d.row_stride[0];
+    In xs = In(), ys = In();
+    if (!x_col) xs = xr ? xr[0] : scalar_as<In>(xv);
+    if (F::kArity == 2 && !y_col) ys = yr ? yr[0] : scalar_as<In>(yv);
+    PIn a[UNROLL], b[UNROLL];
+    if (x_col && !x_rowinv) {
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u)
+        if (full[u]) a[u] = ld_stream(reinterpret_cast<const PIn *>(xr + c0 + (int64_t)u * kThreads * E));
+    }
+    if (y_col && !y_rowinv) {
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u)
+        if (full[u]) b[u] = ld_stream(reinterpret_cast<const PIn *>(yr + c0 + (int64_t)u * kThreads * E));
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int64_t c = c0 + (int64_t)u * kThreads * E;
+      if (full[u]) {
+        POut rr;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const In av = !x_col ? xs : (x_rowinv ? ha[u].v[e] : a[u].v[e]);
+          const In bv = (F::kArity == 2) ? (!y_col ? ys : (y_rowinv ? hb[u].v[e] : b[u].v[e])) : ys;
+          rr.v[e] = apply(f, av, bv);
+        }
+        st_stream(reinterpret_cast<POut *>(orow + c), rr);
+      } else {
+        for (int e = 0; e < E && c + e < d.ncols; ++e) {
+          const In av = !x_col ? xs : xr[c + e];
+          const In bv = (F::kArity == 2 && y_col) ? yr[c + e] : ys;
+          orow[c + e] = apply(f, av, bv);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ generic nd kernel
+template <class F, int UNROLL>
+__global__ void __launch_bounds__(kThreads)
+k_map_nd(size_t n, NdDesc d, const typename F::In *x, const typename F::In *y,
+         typename F::Out *out, Scalar64 xv, Scalar64 yv, F f) {
+  using In = typename F::In;
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  for (size_t i0 = (size_t)blockIdx.x * kThreads + threadIdx.x; i0 < n; i0 += stride * UNROLL) {
+    In a[UNROLL], b[UNROLL];
+    int64_t oo[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const size_t i = i0 + (size_t)u * stride;
+      if (i < n) {
+        int64_t ox = 0, oy = 0, o = 0;
+        if (d.rank <= 1) {
+          o = (int64_t)i * d.stride[0][0];
+          ox = (int64_t)i * d.stride[1][0];
+          oy = (int64_t)i * d.stride[2][0];
+        } else {
+          size_t rem = i;
+          for (int ax = d.rank - 1; ax > 0; --ax) {
+            const size_t q = rem / (size_t)d.dims[ax];
+            const int64_t k = (int64_t)(rem - q * (size_t)d.dims[ax]);
+            rem = q;
+            o += k * d.stride[0][ax];
+            ox += k * d.stride[1][ax];
+            oy += k * d.stride[2][ax];
+          }
+          o += (int64_t)rem * d.stride[0][0];
+          ox += (int64_t)rem * d.stride[1][0];
+          oy += (int64_t)rem * d.stride[2][0];
+        }
+        oo[u] = o;
+        a[u] = x ? x[ox] : scalar_as<In>(xv);
+        if (F::kArity == 2) b[u] = y ? y[oy] : scalar_as<In>(yv);
+        else b[u] = In();
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const size_t i = i0 + (size_t)u * stride;
+      if (i < n) out[oo[u]] = apply(f, a[u], b[u]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ launcher
+// Problem statement shared by every map entry point (BMAS strided call == rank-1 problem).
+struct MapProblem {
+  int rank;                          // already coalesced over (out, x, y)
+  int64_t dims[NUK_MAX_RANK];
+  int64_t so[NUK_MAX_RANK], sx[NUK_MAX_RANK], sy[NUK_MAX_RANK];
+  const void *x, *y;                 // nullptr => scalar by value (xv / yv)
+  void *out;
+  Scalar64 xv, yv;
+  cudaStream_t stream;
+};
+
+int build_problem(MapProblem *p, int arity, int rank, const int64_t *dims, const int64_t *sx,
+                  const int64_t *sy, const int64_t *so);
+
+template <class F> int launch_map(const MapProblem &p, F f = F()) {
+  using In = typename F::In;
+  using Out = typename F::Out;
+  using P = PackOf<F>;
+  constexpr int E = P::E;
+  constexpr int UNROLL = 4;
+  const DeviceInfo *dev = device_info();
+  if (!dev) return nuk_last_status();
+
+  size_t n = 1;
+  for (int a = 0; a < p.rank; ++a) n *= (size_t)p.dims[a];
+  if (n == 0) return NUK_OK;
+  const In *x = static_cast<const In *>(p.x);
+  const In *y = static_cast<const In *>(p.y);
+  Out *out = static_cast<Out *>(p.out);
+  const bool binary = F::kArity == 2;
+  const int last = p.rank - 1;
+
+  auto vec_ok_in = [&](const In *ptr, int64_t inner_stride) {
+    return ptr == nullptr || inner_stride == 0 || aligned_to(ptr, sizeof(typename P::PIn));
+  };
+
+  // ---- flat: rank <= 1, out stride 1, inputs stride 1 or 0
+  if (p.rank <= 1) {
+    const int64_t so = p.rank ? p.so[0] : 1, sx = p.rank ? p.sx[0] : 0, sy = p.rank ? p.sy[0] : 0;
+    const bool xs = (x == nullptr) || sx == 0 || p.rank == 0;
+    const bool ys = !binary || (y == nullptr) || sy == 0 || p.rank == 0;
+    if (so == 1 && (xs || sx == 1) && (ys || sy == 1) && aligned_to(out, sizeof(typename P::POut)) &&
+        (xs || vec_ok_in(x, 1)) && (ys || vec_ok_in(y, 1))) {
+      const size_t tiles = n / E / ((size_t)kThreads * UNROLL) + 1;
+      const int grid = grid_for(tiles, (int)option("grid_mult"));
+      k_map_flat<F, UNROLL><<<grid, kThreads, 0, p.stream>>>(n, x, y, out, xs ? 1 : 0, ys ? 1 : 0,
+                                                             p.xv, p.yv, f);
+      return post_launch("k_map_flat");
+    }
+  }
+  // ---- rows: rank >= 2, inner axis contiguous for out, inputs 1/0 along it
+  if (p.rank >= 2 && p.so[last] == 1 && (x == nullptr || p.sx[last] == 1 || p.sx[last] == 0) &&
+      (!binary || y == nullptr || p.sy[last] == 1 || p.sy[last] == 0) && p.dims[last] >= 64) {
+    // vector path needs every row start 16B-aligned for every vector operand
+    bool ok = aligned_to(out, sizeof(typename P::POut));
+    auto rows_aligned = [&](const int64_t *st, size_t elt) {
+      for (int a = 0; a < last; ++a)
+        if (((st[a] * (int64_t)elt) & 15) != 0) return false;
+      return true;
+    };
+    ok = ok && rows_aligned(p.so, sizeof(Out));
+    if (x && p.sx[last] == 1) ok = ok && aligned_to(x, sizeof(typename P::PIn)) && rows_aligned(p.sx, sizeof(In));
+    if (binary && y && p.sy[last] == 1)
+      ok = ok && aligned_to(y, sizeof(typename P::PIn)) && rows_aligned(p.sy, sizeof(In));
+    size_t outer = 1;
+    for (int a = 0; a < last - 1; ++a) outer *= (size_t)p.dims[a];
+    if (ok) {
+      RowsDesc d;
+      memset(&d, 0, sizeof(d));
+      d.ncols = p.dims[last];
+      d.nrows = p.dims[last - 1];
+      d.row_stride[0] = p.so[last - 1];
+      d.row_stride[1] = x ? p.sx[last - 1] : 0;
+      d.row_stride[2] = (binary && y) ? p.sy[last - 1] : 0;
+      d.col_stride[0] = 1;
+      d.col_stride[1] = (x && p.sx[last] == 1) ? 1 : 0;
+      d.col_stride[2] = (binary && y && p.sy[last] == 1) ? 1 : 0;
+      d.nouter = last - 1;
+      for (int a = 0; a < d.nouter; ++a) {
+        d.odims[a] = p.dims[a];
+        d.ostride[0][a] = p.so[a];
+        d.ostride[1][a] = x ? p.sx[a] : 0;
+        d.ostride[2][a] = (binary && y) ? p.sy[a] : 0;
+      }
+      const int64_t col_tile = (int64_t)kThreads * UNROLL * E;
+      const int64_t col_tiles = (d.ncols + col_tile - 1) / col_tile;
+      // group rows so that the grid still covers the chip ~8x over
+      const int64_t want_ctas = (int64_t)dev->sm_count * 8;
+      int64_t rpc = (int64_t)((double)col_tiles * (double)d.nrows * (double)outer / (double)want_ctas);
+      if (rpc < 1) rpc = 1;
+      if (rpc > 32) rpc = 32;
+      if (rpc > d.nrows) rpc = d.nrows;
+      d.rows_per_cta = (int)rpc;
+      const int64_t row_groups = (d.nrows + rpc - 1) / rpc;
+      const size_t gy = (size_t)row_groups * outer;
+      if (col_tiles <= 65535 && gy <= 0x7fffffffu) {
+        dim3 grid((unsigned)gy, (unsigned)col_tiles);
+        k_map_rows<F, UNROLL><<<grid, kThreads, 0, p.stream>>>(d, x, y, out, p.xv, p.yv, f);
+        return post_launch("k_map_rows");
+      }
+    }
+  }
+  // ---- generic
+  {
+    NdDesc d;
+    memset(&d, 0, sizeof(d));
+    d.rank = p.rank;
+    for (int a = 0; a < p.rank; ++a) {
+      d.dims[a] = p.dims[a];
+      d.stride[0][a] = p.so[a];
+      d.stride[1][a] = x ? p.sx[a] : 0;
+      d.stride[2][a] = (binary && y) ? p.sy[a] : 0;
+    }
+    const size_t blocks = (n + (size_t)kThreads * UNROLL - 1) / ((size_t)kThreads * UNROLL);
+    const int grid = grid_for(blocks, (int)option("grid_mult"));
+    k_map_nd<F, UNROLL><<<grid, kThreads, 0, p.stream>>>(n, d, x, y, out, p.xv, p.yv, f);
+    return post_launch("k_map_nd");
+  }
+}
+
+}  // namespace nuk

@@ -1,0 +1,55 @@
+// trans_f32.cu -- single-float transcendental maps (nu:sin ... nu:exp nu:log nu:expt nu::atan2),
+// table src/transcendental/package.lisp:63-84.  Kernels are the generic map kernels of map.cuh
+// instantiated with the functors below; the math is in nukmath_f32.cuh / nukmath_f64.cuh.
+#include "dispatch.cuh"
+#include "nukmath_f32.cuh"
+#include "nukmath_f64.cuh"
+
+namespace nuk {
+
+#define NUK_F32_UNARY(Name, FN)                         \
+  struct Name {                                         \
+    using In = float; using Out = float;                \
+    static constexpr int kArity = 1;                    \
+    NUK_D float operator()(float a) const { return nukmath::FN(a); } \
+  };
+#define NUK_F32_BINARY(Name, FN)                        \
+  struct Name {                                         \
+    using In = float; using Out = float;                \
+    static constexpr int kArity = 2;                    \
+    NUK_D float operator()(float a, float b) const { return nukmath::FN(a, b); } \
+  };
+NUK_F32_UNARY(SinF, sin_f32) NUK_F32_UNARY(CosF, cos_f32) NUK_F32_UNARY(TanF, tan_f32)
+NUK_F32_UNARY(AsinF, asin_f32) NUK_F32_UNARY(AcosF, acos_f32) NUK_F32_UNARY(AtanF, atan_f32)
+NUK_F32_UNARY(SinhF, sinh_f32) NUK_F32_UNARY(CoshF, cosh_f32) NUK_F32_UNARY(TanhF, tanh_f32)
+NUK_F32_UNARY(AsinhF, asinh_f32) NUK_F32_UNARY(AcoshF, acosh_f32) NUK_F32_UNARY(AtanhF, atanh_f32)
+NUK_F32_UNARY(ExpF, exp_f32) NUK_F32_UNARY(LogF, log_f32)
+NUK_F32_BINARY(PowF, pow_f32) NUK_F32_BINARY(Atan2F, atan2_f32)
+
+int launch_trans_f32(int op, int arity, const MapProblem &p) {
+  if (arity == 2) {
+    if (op == NUK_POW) return launch_map<PowF>(p);
+    if (op == NUK_ATAN2) return launch_map<Atan2F>(p);
+  } else {
+    switch (op) {
+      case NUK_SIN: return launch_map<SinF>(p);
+      case NUK_COS: return launch_map<CosF>(p);
+      case NUK_TAN: return launch_map<TanF>(p);
+      case NUK_ASIN: return launch_map<AsinF>(p);
+      case NUK_ACOS: return launch_map<AcosF>(p);
+      case NUK_ATAN: return launch_map<AtanF>(p);
+      case NUK_SINH: return launch_map<SinhF>(p);
+      case NUK_COSH: return launch_map<CoshF>(p);
+      case NUK_TANH: return launch_map<TanhF>(p);
+      case NUK_ASINH: return launch_map<AsinhF>(p);
+      case NUK_ACOSH: return launch_map<AcoshF>(p);
+      case NUK_ATANH: return launch_map<AtanhF>(p);
+      case NUK_EXP: return launch_map<ExpF>(p);
+      case NUK_LOG: return launch_map<LogF>(p);
+    }
+  }
+  set_error(NUK_ERR_UNSUPPORTED, "no single-float transcendental kernel for op %d (arity %d)", op, arity);
+  return NUK_ERR_UNSUPPORTED;
+}
+
+}  // namespace nuk

@@ -1,0 +1,52 @@
+// trans_f64.cu -- double-float transcendental maps, table src/transcendental/package.lisp:63-84.
+#include "dispatch.cuh"
+#include "nukmath_f64.cuh"
+
+namespace nuk {
+
+#define NUK_F64_UNARY(Name, FN)                         \
+  struct Name {                                         \
+    using In = double; using Out = double;              \
+    static constexpr int kArity = 1;                    \
+    NUK_D double operator()(double a) const { return nukmath::FN(a); } \
+  };
+#define NUK_F64_BINARY(Name, FN)                        \
+  struct Name {                                         \
+    using In = double; using Out = double;              \
+    static constexpr int kArity = 2;                    \
+    NUK_D double operator()(double a, double b) const { return nukmath::FN(a, b); } \
+  };
+NUK_F64_UNARY(SinD, sin_f64) NUK_F64_UNARY(CosD, cos_f64) NUK_F64_UNARY(TanD, tan_f64)
+NUK_F64_UNARY(AsinD, asin_f64) NUK_F64_UNARY(AcosD, acos_f64) NUK_F64_UNARY(AtanD, atan_f64)
+NUK_F64_UNARY(SinhD, sinh_f64) NUK_F64_UNARY(CoshD, cosh_f64) NUK_F64_UNARY(TanhD, tanh_f64)
+NUK_F64_UNARY(AsinhD, asinh_f64) NUK_F64_UNARY(AcoshD, acosh_f64) NUK_F64_UNARY(AtanhD, atanh_f64)
+NUK_F64_UNARY(ExpD, exp_f64) NUK_F64_UNARY(LogD, log_f64)
+NUK_F64_BINARY(PowD, pow_f64) NUK_F64_BINARY(Atan2D, atan2_f64)
+
+int launch_trans_f64(int op, int arity, const MapProblem &p) {
+  if (arity == 2) {
+    if (op == NUK_POW) return launch_map<PowD>(p);
+    if (op == NUK_ATAN2) return launch_map<Atan2D>(p);
+  } else {
+    switch (op) {
+      case NUK_SIN: return launch_map<SinD>(p);
+      case NUK_COS: return launch_map<CosD>(p);
+      case NUK_TAN: return launch_map<TanD>(p);
+      case NUK_ASIN: return launch_map<AsinD>(p);
+      case NUK_ACOS: return launch_map<AcosD>(p);
+      case NUK_ATAN: return launch_map<AtanD>(p);
+      case NUK_SINH: return launch_map<SinhD>(p);
+      case NUK_COSH: return launch_map<CoshD>(p);
+      case NUK_TANH: return launch_map<TanhD>(p);
+      case NUK_ASINH: return launch_map<AsinhD>(p);
+      case NUK_ACOSH: return launch_map<AcoshD>(p);
+      case NUK_ATANH: return launch_map<AtanhD>(p);
+      case NUK_EXP: return launch_map<ExpD>(p);
+      case NUK_LOG: return launch_map<LogD>(p);
+    }
+  }
+  set_error(NUK_ERR_UNSUPPORTED, "no double-float transcendental kernel for op %d (arity %d)", op, arity);
+  return NUK_ERR_UNSUPPORTED;
+}
+
+}  // namespace nuk

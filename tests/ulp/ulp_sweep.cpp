@@ -1,0 +1,169 @@
+// tests/ulp/ulp_sweep.cpp -- TEST INFRASTRUCTURE.
+// Compiles the product math headers (numericals_b200/csrc/nukmath_f32.cuh, nukmath_f64.cuh) for
+// the HOST and sweeps them against (a) a higher-precision truth (glibc double for f32, glibc
+// long double for f64) and (b) the SLEEF 3.8 *_u10 functions the oracle uses (fixed AVX2 entry
+// points from libtorch_cpu.so), reporting the max error in ULP and the max integer ULP distance
+// to SLEEF.  f32 unary functions are swept EXHAUSTIVELY (all 2^32 bit patterns); f64 and binary
+// functions on dense pseudo-random + edge samples.  The device executes the same IEEE
+// operations in the same order (-fmad=false, explicit fma), so these numbers carry over
+// bit-for-bit; tests/test_transcendental_gpu.py re-checks that on the GPU.
+//
+// usage: ulp_sweep <function> [f32|f64] [lo hi] [count]
+#include <immintrin.h>
+#include <math.h>
+#include <omp.h>
+#include <sleef.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include "../../numericals_b200/csrc/nukmath_f32.cuh"
+#ifdef NUK_HAVE_F64
+#include "../../numericals_b200/csrc/nukmath_f64.cuh"
+#endif
+
+extern "C" {
+__m256 Sleef_sinf8_u10avx2(__m256); __m256 Sleef_cosf8_u10avx2(__m256); __m256 Sleef_tanf8_u10avx2(__m256);
+__m256 Sleef_asinf8_u10avx2(__m256); __m256 Sleef_acosf8_u10avx2(__m256); __m256 Sleef_atanf8_u10avx2(__m256);
+__m256 Sleef_sinhf8_u10avx2(__m256); __m256 Sleef_coshf8_u10avx2(__m256); __m256 Sleef_tanhf8_u10avx2(__m256);
+__m256 Sleef_asinhf8_u10avx2(__m256); __m256 Sleef_acoshf8_u10avx2(__m256); __m256 Sleef_atanhf8_u10avx2(__m256);
+__m256 Sleef_expf8_u10avx2(__m256); __m256 Sleef_logf8_u10avx2(__m256);
+__m256 Sleef_powf8_u10avx2(__m256, __m256); __m256 Sleef_atan2f8_u10avx2(__m256, __m256);
+__m256d Sleef_sind4_u10avx2(__m256d); __m256d Sleef_cosd4_u10avx2(__m256d); __m256d Sleef_tand4_u10avx2(__m256d);
+__m256d Sleef_asind4_u10avx2(__m256d); __m256d Sleef_acosd4_u10avx2(__m256d); __m256d Sleef_atand4_u10avx2(__m256d);
+__m256d Sleef_sinhd4_u10avx2(__m256d); __m256d Sleef_coshd4_u10avx2(__m256d); __m256d Sleef_tanhd4_u10avx2(__m256d);
+__m256d Sleef_asinhd4_u10avx2(__m256d); __m256d Sleef_acoshd4_u10avx2(__m256d); __m256d Sleef_atanhd4_u10avx2(__m256d);
+__m256d Sleef_expd4_u10avx2(__m256d); __m256d Sleef_logd4_u10avx2(__m256d);
+__m256d Sleef_powd4_u10avx2(__m256d, __m256d); __m256d Sleef_atan2d4_u10avx2(__m256d, __m256d);
+}
+
+typedef float (*f32_fn)(float);
+typedef double (*truth32_fn)(double);
+typedef __m256 (*sleef32_fn)(__m256);
+
+struct Fn32 { const char *name; f32_fn mine; truth32_fn truth; sleef32_fn sleef; };
+static const Fn32 kFn32[] = {
+  {"exp", nukmath::exp_f32, exp, Sleef_expf8_u10avx2},
+  {"log", nukmath::log_f32, log, Sleef_logf8_u10avx2},
+  {"sin", nukmath::sin_f32, sin, Sleef_sinf8_u10avx2},
+  {"cos", nukmath::cos_f32, cos, Sleef_cosf8_u10avx2},
+  {"tanh", nukmath::tanh_f32, tanh, Sleef_tanhf8_u10avx2},
+#ifdef NUK_HAVE_F64
+  {"tan", nukmath::tan_f32, tan, Sleef_tanf8_u10avx2},
+  {"asin", nukmath::asin_f32, asin, Sleef_asinf8_u10avx2},
+  {"acos", nukmath::acos_f32, acos, Sleef_acosf8_u10avx2},
+  {"atan", nukmath::atan_f32, atan, Sleef_atanf8_u10avx2},
+  {"sinh", nukmath::sinh_f32, sinh, Sleef_sinhf8_u10avx2},
+  {"cosh", nukmath::cosh_f32, cosh, Sleef_coshf8_u10avx2},
+  {"asinh", nukmath::asinh_f32, asinh, Sleef_asinhf8_u10avx2},
+  {"acosh", nukmath::acosh_f32, acosh, Sleef_acoshf8_u10avx2},
+  {"atanh", nukmath::atanh_f32, atanh, Sleef_atanhf8_u10avx2},
+#endif
+};
+
+static inline int32_t ord32(float f) {  // monotone integer key
+  int32_t i; memcpy(&i, &f, 4);
+  return i < 0 ? (int32_t)0x80000000 - i : i;
+}
+static inline int64_t ord64(double f) {
+  int64_t i; memcpy(&i, &f, 8);
+  return i < 0 ? (int64_t)0x8000000000000000LL - i : i;
+}
+
+// error of `got` against the exact value t, in units of the f32 ULP at t
+static inline double ulp_err32(float got, double t) {
+  if (t != t) return (got != got) ? 0.0 : 1e9;
+  if (got != got) return 1e9;
+  if (isinf(t)) return (got == (float)t) ? 0.0 : 1e9;
+  double at = fabs(t);
+  int e = at < 0x1p-126 ? -126 : ilogb(at);
+  if (e > 127) e = 127;
+  const double ulp = ldexp(1.0, e - 23);
+  if (isinf(got)) {
+    const double lim = 0x1.ffffffp127;  // FLT_MAX + half ulp: rounds to inf at or above
+    if (at >= lim && ((got > 0) == (t > 0))) return 0.0;
+    return fabs(ldexp(1.0, 128) - at) / ulp;
+  }
+  return fabs((double)got - t) / ulp;
+}
+
+static int sweep32(const Fn32 &fn, uint64_t lo_bits, uint64_t hi_bits) {
+  const int T = omp_get_max_threads();
+  double *worst = (double *)calloc(T, sizeof(double));
+  uint32_t *worst_at = (uint32_t *)calloc(T, sizeof(uint32_t));
+  int64_t *sdist = (int64_t *)calloc(T, sizeof(int64_t));
+  uint32_t *sdist_at = (uint32_t *)calloc(T, sizeof(uint32_t));
+  uint64_t *not_cr = (uint64_t *)calloc(T, sizeof(uint64_t));
+  double *sworst = (double *)calloc(T, sizeof(double));
+  const uint64_t nblk = (hi_bits - lo_bits + 7) / 8;
+#pragma omp parallel for schedule(dynamic, 1 << 16)
+  for (uint64_t blk = 0; blk < nblk; ++blk) {
+    const int tid = omp_get_thread_num();
+    float xs[8], ss[8];
+    for (int k = 0; k < 8; ++k) {
+      uint64_t b = lo_bits + blk * 8 + k;
+      if (b >= hi_bits) b = hi_bits - 1;
+      uint32_t u = (uint32_t)b;
+      memcpy(&xs[k], &u, 4);
+    }
+    _mm256_storeu_ps(ss, fn.sleef(_mm256_loadu_ps(xs)));
+    for (int k = 0; k < 8; ++k) {
+      const float x = xs[k];
+      const float got = fn.mine(x);
+      const double t = fn.truth((double)x);
+      const double e = ulp_err32(got, t);
+      uint32_t u; memcpy(&u, &x, 4);
+      if (e > worst[tid]) { worst[tid] = e; worst_at[tid] = u; }
+      if (got != (float)t && !(got != got)) not_cr[tid]++;
+      const double es = ulp_err32(ss[k], t);
+      if (es > sworst[tid] && es < 1e8) sworst[tid] = es;
+      if (!(got != got) && !(ss[k] != ss[k])) {
+        int64_t d = (int64_t)ord32(got) - (int64_t)ord32(ss[k]);
+        if (d < 0) d = -d;
+        if (d > sdist[tid]) { sdist[tid] = d; sdist_at[tid] = u; }
+      } else if ((got != got) != (ss[k] != ss[k])) {
+        // NaN-ness disagreement with SLEEF: report as a huge distance unless truth agrees with us
+        if ((t != t) != (got != got)) { sdist[tid] = 1 << 30; sdist_at[tid] = u; }
+      }
+    }
+  }
+  double w = 0, sw = 0; uint32_t wa = 0, sa = 0; int64_t sd = 0; uint64_t ncr = 0;
+  for (int i = 0; i < T; ++i) {
+    if (worst[i] > w) { w = worst[i]; wa = worst_at[i]; }
+    if (sdist[i] > sd) { sd = sdist[i]; sa = sdist_at[i]; }
+    if (sworst[i] > sw) sw = sworst[i];
+    ncr += not_cr[i];
+  }
+  float wx, sx; memcpy(&wx, &wa, 4); memcpy(&sx, &sa, 4);
+  printf("{\"fn\": \"%s\", \"type\": \"f32\", \"inputs\": %llu, \"max_ulp\": %.4f, \"worst_x\": \"%a\", "
+         "\"not_correctly_rounded\": %llu, \"max_ulp_dist_vs_sleef_u10\": %lld, \"dist_x\": \"%a\", "
+         "\"sleef_u10_max_ulp\": %.4f}\n",
+         fn.name, (unsigned long long)(hi_bits - lo_bits), w, wx, (unsigned long long)ncr,
+         (long long)sd, sx, sw);
+  return (w < 1.0 && sd <= 1) ? 0 : 1;
+}
+
+#ifdef NUK_HAVE_F64
+#include "ulp_sweep_f64.inc"
+#endif
+
+int main(int argc, char **argv) {
+  if (argc < 2) {
+    fprintf(stderr, "usage: %s <fn|all> [f32|f64] [lo_bits hi_bits]\n", argv[0]);
+    return 2;
+  }
+  const std::string which = argv[1];
+  const std::string type = argc > 2 ? argv[2] : "f32";
+  int rc = 0;
+  if (type == "f32") {
+    uint64_t lo = 0, hi = 1ull << 32;
+    if (argc > 4) { lo = strtoull(argv[3], 0, 0); hi = strtoull(argv[4], 0, 0); }
+    for (const Fn32 &f : kFn32)
+      if (which == "all" || which == f.name) rc |= sweep32(f, lo, hi);
+  }
+#ifdef NUK_HAVE_F64
+  else rc = sweep64_main(which, argc, argv);
+#endif
+  return rc;
+}
