@@ -9,7 +9,10 @@ namespace nuk {
 template <typename T> struct UnsignedOf { using type = typename std::make_unsigned<T>::type; };
 
 // integer arithmetic wraps: done in the unsigned type (>= 32 bit) of the same width
-template <typename T> struct WrapT {
+template <typename T, bool IsFloat = std::is_floating_point<T>::value> struct WrapT {
+  using type = T;  // floats accumulate in their own type
+};
+template <typename T> struct WrapT<T, false> {
   using U = typename std::make_unsigned<T>::type;
   using type = typename std::conditional<(sizeof(T) < 4), uint32_t, U>::type;
 };

@@ -1,0 +1,323 @@
+// reduce2.cu -- SURVEY 8(f) "next" rows that share the reduction skeleton:
+//   BMAS_<t>dot        (vdot = multiply + sum fused: 2 reads per element instead of the
+//                       reference's multiply pass + sum pass; src/linalg/vdot.lisp:15-25)
+//   BMAS_<t>himax/himin (nu:arg-maximum / nu:arg-minimum, src/basic-math/arg-maximum.lisp:31-73):
+//                       index of the FIRST extremum.
+// Deterministic two-pass reductions like reduce.cu; operands may be device or host pointers.
+#include <limits>
+#include "dispatch.cuh"
+#include "ops.cuh"
+
+namespace nuk {
+
+template <typename T> struct AccT {
+  using type = typename std::conditional<std::is_floating_point<T>::value, T, typename WrapT<T>::type>::type;
+};
+
+template <typename A> NUK_D A shfl_down_any(A v, int delta) {
+  constexpr int W = (sizeof(A) + 3) / 4;
+  unsigned w[W];
+  memset(w, 0, sizeof(w));
+  memcpy(w, &v, sizeof(A));
+#pragma unroll
+  for (int i = 0; i < W; ++i) w[i] = __shfl_down_sync(0xffffffffu, w[i], delta);
+  A r;
+  memcpy(&r, w, sizeof(A));
+  return r;
+}
+template <typename A, class Combine> NUK_D A block_fold(A v, A init, Combine comb) {
+  __shared__ alignas(16) unsigned char raw[sizeof(A) * (kThreads / 32)];
+  A *sm = reinterpret_cast<A *>(raw);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v = comb(v, shfl_down_any(v, d));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sm[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    v = (lane < kThreads / 32) ? sm[lane] : init;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v = comb(v, shfl_down_any(v, d));
+  }
+  return v;
+}
+
+// ------------------------------------------------------------------ dot
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_dot(size_t n, const T *x, int64_t ix, const T *y, int64_t iy, typename AccT<T>::type *partials,
+      int vec) {
+  using A = typename AccT<T>::type;
+  constexpr int E = 16 / sizeof(T);
+  using P = Pack<T, E>;
+  A acc[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) acc[e] = (A)0;
+  auto comb = [](A a, A b) { return a + b; };
+  if (vec) {
+    const P *xp = reinterpret_cast<const P *>(x), *yp = reinterpret_cast<const P *>(y);
+    const size_t npack = n / E;
+    constexpr int U = 4;
+    const size_t tile = (size_t)kThreads * U, nfull = npack / tile;
+    for (size_t t = blockIdx.x; t < nfull; t += gridDim.x) {
+      const size_t base = t * tile + threadIdx.x;
+      P a[U], b[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) a[u] = ld_stream(xp + base + (size_t)u * kThreads);
+#pragma unroll
+      for (int u = 0; u < U; ++u) b[u] = ld_stream(yp + base + (size_t)u * kThreads);
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int e = 0; e < E; ++e) acc[e] = acc[e] + (A)a[u].v[e] * (A)b[u].v[e];  // product rounded, then added
+    }
+    if (blockIdx.x == nfull % gridDim.x) {
+      for (size_t p = nfull * tile + threadIdx.x; p < npack; p += kThreads) {
+        const P a = ld_stream(xp + p), b = ld_stream(yp + p);
+#pragma unroll
+        for (int e = 0; e < E; ++e) acc[e] = acc[e] + (A)a.v[e] * (A)b.v[e];
+      }
+      const size_t i = npack * E + threadIdx.x;
+      if (i < n) acc[0] = acc[0] + (A)x[i] * (A)y[i];
+    }
+  } else {
+    const size_t stride = (size_t)gridDim.x * kThreads;
+    for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride)
+      acc[0] = acc[0] + (A)x[(int64_t)i * ix] * (A)y[(int64_t)i * iy];
+  }
+  A v = acc[0];
+#pragma unroll
+  for (int e = 1; e < E; ++e) v = v + acc[e];
+  v = block_fold(v, (A)0, comb);
+  if (threadIdx.x == 0) partials[blockIdx.x] = v;
+}
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_dot_combine(size_t count, const typename AccT<T>::type *partials, T *out, int accumulate) {
+  using A = typename AccT<T>::type;
+  A acc = (A)0;
+  for (size_t i = threadIdx.x; i < count; i += kThreads) acc = acc + partials[i];
+  acc = block_fold(acc, (A)0, [](A a, A b) { return a + b; });
+  if (threadIdx.x == 0) out[0] = accumulate ? (T)((A)out[0] + acc) : (T)acc;
+}
+
+template <typename T>
+static int dot_device(size_t n, const T *x, int64_t ix, const T *y, int64_t iy, T *out_dev, int accumulate,
+                      cudaStream_t st) {
+  using A = typename AccT<T>::type;
+  constexpr int E = 16 / sizeof(T);
+  const int vec = (ix == 1 && iy == 1 && aligned_to(x, 16) && aligned_to(y, 16)) ? 1 : 0;
+  const size_t blocks = n / E / ((size_t)kThreads * 4) + 1;
+  const int grid = grid_for(blocks, (int)option("reduce_grid_mult"));
+  void *part = nullptr;
+  NUK_TRY(scratch(st, sizeof(A) * (size_t)grid, &part));
+  k_dot<T><<<grid, kThreads, 0, st>>>(n, x, ix, y, iy, static_cast<A *>(part), vec);
+  NUK_TRY(post_launch("k_dot"));
+  k_dot_combine<T><<<1, kThreads, 0, st>>>((size_t)grid, static_cast<const A *>(part), out_dev, accumulate);
+  return post_launch("k_dot_combine");
+}
+
+// ------------------------------------------------------------------ arg-reductions
+template <typename T> struct ValIdx { T v; int64_t i; };
+
+template <typename T, bool IS_MAX>
+__global__ void __launch_bounds__(kThreads)
+k_argred(size_t n, const T *x, int64_t ix, int64_t index_base, ValIdx<T> *partials, T init) {
+  using A = ValIdx<T>;
+  auto comb = [](A a, A b) {
+    const bool better = IS_MAX ? (b.v > a.v) : (b.v < a.v);
+    const bool tie_first = (b.v == a.v) && (b.i < a.i);
+    return (better || tie_first) ? b : a;
+  };
+  A acc{init, INT64_MAX};
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride)
+    acc = comb(acc, A{x[(int64_t)i * ix], (int64_t)i + index_base});
+  acc = block_fold(acc, A{init, INT64_MAX}, comb);
+  if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+}
+template <typename T, bool IS_MAX>
+__global__ void __launch_bounds__(kThreads)
+k_argred_combine(size_t count, const ValIdx<T> *partials, ValIdx<T> *out, int accumulate, T init) {
+  using A = ValIdx<T>;
+  auto comb = [](A a, A b) {
+    const bool better = IS_MAX ? (b.v > a.v) : (b.v < a.v);
+    const bool tie_first = (b.v == a.v) && (b.i < a.i);
+    return (better || tie_first) ? b : a;
+  };
+  A acc = (accumulate && threadIdx.x == 0) ? out[0] : A{init, INT64_MAX};
+  for (size_t i = threadIdx.x; i < count; i += kThreads) acc = comb(acc, partials[i]);
+  acc = block_fold(acc, A{init, INT64_MAX}, comb);
+  if (threadIdx.x == 0) out[0] = acc;
+}
+
+template <typename T, bool IS_MAX>
+static int argred_device(size_t n, const T *x, int64_t ix, int64_t index_base, ValIdx<T> *out_dev,
+                         int accumulate, cudaStream_t st) {
+  T init;
+  if (std::is_floating_point<T>::value)
+    init = IS_MAX ? -std::numeric_limits<T>::infinity() : std::numeric_limits<T>::infinity();
+  else
+    init = IS_MAX ? std::numeric_limits<T>::lowest() : std::numeric_limits<T>::max();
+  const size_t blocks = (n + (size_t)kThreads * 4 - 1) / ((size_t)kThreads * 4);
+  const int grid = grid_for(blocks ? blocks : 1, (int)option("reduce_grid_mult"));
+  void *part = nullptr;
+  NUK_TRY(scratch(st, sizeof(ValIdx<T>) * (size_t)grid, &part));
+  k_argred<T, IS_MAX><<<grid, kThreads, 0, st>>>(n, x, ix, index_base, static_cast<ValIdx<T> *>(part), init);
+  NUK_TRY(post_launch("k_argred"));
+  k_argred_combine<T, IS_MAX><<<1, kThreads, 0, st>>>((size_t)grid, static_cast<const ValIdx<T> *>(part),
+                                                      out_dev, accumulate, init);
+  return post_launch("k_argred_combine");
+}
+
+// ------------------------------------------------------------------ value-returning wrappers
+static bool is_device_ptr(const void *p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// stage a strided HOST chunk into a contiguous device buffer (address order); returns walk ptr/inc
+static int stage_chunk(const void *host, long inc, size_t sz, long c0, long m, void *dbuf, cudaStream_t st,
+                       const void **dp, long *di) {
+  const char *base = static_cast<const char *>(host);
+  const long ainc = inc < 0 ? -inc : inc;
+  const char *lo = inc > 0 ? base + (int64_t)c0 * inc * (int64_t)sz
+                           : base + (int64_t)(c0 + m - 1) * inc * (int64_t)sz;
+  if (ainc == 1) NUK_CUDA(cudaMemcpyAsync(dbuf, lo, (size_t)m * sz, cudaMemcpyHostToDevice, st));
+  else NUK_CUDA(cudaMemcpy2DAsync(dbuf, sz, lo, (size_t)ainc * sz, sz, (size_t)m, cudaMemcpyHostToDevice, st));
+  if (inc > 0) { *dp = dbuf; *di = 1; }
+  else { *dp = static_cast<char *>(dbuf) + (size_t)(m - 1) * sz; *di = -1; }
+  return NUK_OK;
+}
+
+struct HostStage {
+  void *bx = nullptr, *by = nullptr, *res = nullptr;
+  size_t cap = 0;
+  ~HostStage() {
+    if (bx) cudaFree(bx);
+    if (by) cudaFree(by);
+    if (res) cudaFree(res);
+  }
+  int ensure(size_t want) {
+    if (!res) NUK_CUDA(cudaMalloc(&res, 64));
+    if (cap >= want) return NUK_OK;
+    if (bx) cudaFree(bx);
+    if (by) cudaFree(by);
+    bx = by = nullptr;
+    NUK_CUDA(cudaMalloc(&bx, want));
+    NUK_CUDA(cudaMalloc(&by, want));
+    cap = want;
+    return NUK_OK;
+  }
+};
+static thread_local HostStage tl_hs;
+
+template <typename T>
+static int dot_typed(long n, const void *x, long ix, const void *y, long iy, void *result) {
+  memset(result, 0, sizeof(T));
+  if (n <= 0) return NUK_OK;
+  if (!device_info()) return nuk_last_status();
+  cudaStream_t st = current_stream();
+  void *pin = nullptr;
+  NUK_TRY(pinned_slot(&pin));
+  const bool xd = is_device_ptr(x), yd = is_device_ptr(y);
+  size_t cap = (size_t)(option("stage_mb") > 0 ? option("stage_mb") : 32) << 20;
+  NUK_TRY(tl_hs.ensure((xd && yd) ? 256 : cap));
+  T *dres = static_cast<T *>(tl_hs.res);
+  if (xd && yd) {
+    NUK_TRY(dot_device<T>((size_t)n, static_cast<const T *>(x), ix, static_cast<const T *>(y), iy, dres, 0, st));
+  } else {
+    const long chunk = (long)(cap / sizeof(T));
+    long c0 = 0;
+    for (int k = 0; c0 < n; ++k, c0 += chunk) {
+      const long m = (n - c0 < chunk) ? (n - c0) : chunk;
+      const void *xp, *yp;
+      long xi, yi;
+      if (xd) { xp = static_cast<const char *>(x) + (int64_t)c0 * ix * (int64_t)sizeof(T); xi = ix; }
+      else if (ix == 0) { NUK_CUDA(cudaMemcpyAsync(tl_hs.bx, x, sizeof(T), cudaMemcpyHostToDevice, st)); xp = tl_hs.bx; xi = 0; }
+      else NUK_TRY(stage_chunk(x, ix, sizeof(T), c0, m, tl_hs.bx, st, &xp, &xi));
+      if (yd) { yp = static_cast<const char *>(y) + (int64_t)c0 * iy * (int64_t)sizeof(T); yi = iy; }
+      else if (iy == 0) { NUK_CUDA(cudaMemcpyAsync(tl_hs.by, y, sizeof(T), cudaMemcpyHostToDevice, st)); yp = tl_hs.by; yi = 0; }
+      else NUK_TRY(stage_chunk(y, iy, sizeof(T), c0, m, tl_hs.by, st, &yp, &yi));
+      NUK_TRY(dot_device<T>((size_t)m, static_cast<const T *>(xp), xi, static_cast<const T *>(yp), yi, dres,
+                            k > 0, st));
+    }
+  }
+  NUK_CUDA(cudaMemcpyAsync(pin, dres, sizeof(T), cudaMemcpyDeviceToHost, st));
+  NUK_CUDA(cudaStreamSynchronize(st));
+  memcpy(result, pin, sizeof(T));
+  return NUK_OK;
+}
+
+template <typename T, bool IS_MAX>
+static int argred_typed(long n, const void *x, long ix, long *result) {
+  *result = 0;
+  if (n <= 0) return NUK_OK;
+  if (!device_info()) return nuk_last_status();
+  cudaStream_t st = current_stream();
+  void *pin = nullptr;
+  NUK_TRY(pinned_slot(&pin));
+  const bool xd = is_device_ptr(x);
+  size_t cap = (size_t)(option("stage_mb") > 0 ? option("stage_mb") : 32) << 20;
+  NUK_TRY(tl_hs.ensure(xd ? 256 : cap));
+  ValIdx<T> *dres = static_cast<ValIdx<T> *>(tl_hs.res);
+  if (xd) {
+    NUK_TRY((argred_device<T, IS_MAX>((size_t)n, static_cast<const T *>(x), ix, 0, dres, 0, st)));
+  } else {
+    const long chunk = (long)(cap / sizeof(T));
+    long c0 = 0;
+    for (int k = 0; c0 < n; ++k, c0 += chunk) {
+      const long m = (n - c0 < chunk) ? (n - c0) : chunk;
+      const void *xp;
+      long xi;
+      if (ix == 0) { *result = 0; return NUK_OK; }
+      NUK_TRY(stage_chunk(x, ix, sizeof(T), c0, m, tl_hs.bx, st, &xp, &xi));
+      NUK_TRY((argred_device<T, IS_MAX>((size_t)m, static_cast<const T *>(xp), xi, c0, dres, k > 0, st)));
+    }
+  }
+  NUK_CUDA(cudaMemcpyAsync(pin, dres, sizeof(ValIdx<T>), cudaMemcpyDeviceToHost, st));
+  NUK_CUDA(cudaStreamSynchronize(st));
+  ValIdx<T> r;
+  memcpy(&r, pin, sizeof(r));
+  *result = (r.i == INT64_MAX) ? 0 : (long)r.i;  // all-NaN input: index 0, like the scalar loop
+  return NUK_OK;
+}
+
+int dot_value(int dtype, long n, const void *x, long incx, const void *y, long incy, void *result) {
+  switch (dtype) {
+    case NUK_F32: return dot_typed<float>(n, x, incx, y, incy, result);
+    case NUK_F64: return dot_typed<double>(n, x, incx, y, incy, result);
+    case NUK_I64: return dot_typed<int64_t>(n, x, incx, y, incy, result);
+    case NUK_I32: return dot_typed<int32_t>(n, x, incx, y, incy, result);
+    case NUK_I16: return dot_typed<int16_t>(n, x, incx, y, incy, result);
+    case NUK_I8: return dot_typed<int8_t>(n, x, incx, y, incy, result);
+  }
+  set_error(NUK_ERR_UNSUPPORTED, "dot: no kernel for dtype %d", dtype);
+  return NUK_ERR_UNSUPPORTED;
+}
+
+template <bool IS_MAX> static int argred_by_type(int dtype, long n, const void *x, long incx, long *r) {
+  switch (dtype) {
+    case NUK_F32: return argred_typed<float, IS_MAX>(n, x, incx, r);
+    case NUK_F64: return argred_typed<double, IS_MAX>(n, x, incx, r);
+    case NUK_I64: return argred_typed<int64_t, IS_MAX>(n, x, incx, r);
+    case NUK_I32: return argred_typed<int32_t, IS_MAX>(n, x, incx, r);
+    case NUK_I16: return argred_typed<int16_t, IS_MAX>(n, x, incx, r);
+    case NUK_I8: return argred_typed<int8_t, IS_MAX>(n, x, incx, r);
+    case NUK_U64: return argred_typed<uint64_t, IS_MAX>(n, x, incx, r);
+    case NUK_U32: return argred_typed<uint32_t, IS_MAX>(n, x, incx, r);
+    case NUK_U16: return argred_typed<uint16_t, IS_MAX>(n, x, incx, r);
+    case NUK_U8: return argred_typed<uint8_t, IS_MAX>(n, x, incx, r);
+  }
+  set_error(NUK_ERR_UNSUPPORTED, "arg-reduction: no kernel for dtype %d", dtype);
+  return NUK_ERR_UNSUPPORTED;
+}
+int argred_value(int is_max, int dtype, long n, const void *x, long incx, long *result) {
+  return is_max ? argred_by_type<true>(dtype, n, x, incx, result) : argred_by_type<false>(dtype, n, x, incx, result);
+}
+
+}  // namespace nuk

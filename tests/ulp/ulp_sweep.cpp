@@ -118,7 +118,11 @@ static int sweep32(const Fn32 &fn, uint64_t lo_bits, uint64_t hi_bits) {
       if (got != (float)t && !(got != got)) not_cr[tid]++;
       const double es = ulp_err32(ss[k], t);
       if (es > sworst[tid] && es < 1e8) sworst[tid] = es;
-      if (!(got != got) && !(ss[k] != ss[k])) {
+      if (es > 1.0) {
+        // SLEEF itself is outside its u10 bound here (outside its documented domain, e.g.
+        // sinhf beyond +-88.5 or asinhf where x*x overflows): the reference has no valid answer
+        // to be within 1 ULP of; our result is still checked against the truth above.
+      } else if (!(got != got) && !(ss[k] != ss[k])) {
         int64_t d = (int64_t)ord32(got) - (int64_t)ord32(ss[k]);
         if (d < 0) d = -d;
         if (d > sdist[tid]) { sdist[tid] = d; sdist_at[tid] = u; }
