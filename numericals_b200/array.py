@@ -184,3 +184,22 @@ def empty(dims, type=None):
     for d in dims:
         n *= d
     return DenseArray(Storage(n * T.c_size(et)), et, dims)
+
+
+class BorrowedStorage:
+    """Device memory owned by someone else (e.g. a torch CUDA tensor kept alive in `owner`)."""
+
+    def __init__(self, ptr, nbytes, owner=None):
+        self.ptr = int(ptr)
+        self.nbytes = int(nbytes)
+        self.owner = owner
+
+
+def from_pointer(ptr, element_type, dims, owner=None):
+    """Wrap existing device memory (row-major) as a DenseArray without copying."""
+    et = T.normalize(element_type)
+    dims = (dims,) if isinstance(dims, int) else tuple(dims)
+    n = 1
+    for d in dims:
+        n *= d
+    return DenseArray(BorrowedStorage(ptr, n * T.c_size(et), owner), et, dims)
