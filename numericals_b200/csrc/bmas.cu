@@ -121,6 +121,7 @@ static void host_scalar(const Opnd &o, Scalar64 *v) {
 // Launch = int(const MapProblem&)
 template <class Launch>
 static int run_map_1d(int arity, long n, Opnd x, Opnd y, Opnd out, Launch launch) {
+  nuk_clear_error();  // nuk_last_status() describes the most recent BMAS_* call of this thread
   const DeviceInfo *dev = device_info();
   if (!dev) return nuk_last_status();
   if (n <= 0) return NUK_OK;
@@ -213,6 +214,7 @@ static int run_map_1d(int arity, long n, Opnd x, Opnd y, Opnd out, Launch launch
 
 // ------------------------------------------------------------------ reductions by value
 static int reduce_value(int red, int dtype, long n, const void *x, long incx, void *result) {
+  nuk_clear_error();
   const DeviceInfo *dev = device_info();
   if (!dev) return nuk_last_status();
   const size_t sz = dtype_size(dtype);

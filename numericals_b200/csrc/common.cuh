@@ -118,6 +118,10 @@ template <typename P> NUK_D P ld_keep(const P *p) {  // default policy (operand 
 
 inline bool aligned_to(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
+// functors over 8-bit elements may provide a SIMD-in-a-word form (specialised in ops.cuh):
+//   static uint32_t op(uint32_t a, uint32_t b)   -- four elements per call
+template <class F> struct Word4 { static constexpr bool ok = false; };
+
 // ------------------------------------------------------------------ nd descriptor (device side)
 struct NdDesc {
   int rank;                       // <= NUK_MAX_RANK, after coalescing

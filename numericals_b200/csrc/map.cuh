@@ -78,9 +78,21 @@ k_map_flat(size_t n, const typename F::In *x, const typename F::In *y, typename 
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
       POut r;
+      if constexpr (Word4<F>::ok) {
+        // 8-bit operands: four elements per 32-bit SIMD-in-a-word instruction
+        uint32_t wa[4], wb[4], wr[4];
+        if (x_scalar) { wa[0] = wa[1] = wa[2] = wa[3] = (uint32_t)(uint8_t)xs * 0x01010101u; }
+        else memcpy(wa, &a[u], 16);
+        if (F::kArity == 2 && !y_scalar) memcpy(wb, &b[u], 16);
+        else { wb[0] = wb[1] = wb[2] = wb[3] = (uint32_t)(uint8_t)ys * 0x01010101u; }
 #pragma unroll
-      for (int e = 0; e < E; ++e)
-        r.v[e] = apply(f, x_scalar ? xs : a[u].v[e], (F::kArity == 2 && !y_scalar) ? b[u].v[e] : ys);
+        for (int w = 0; w < 4; ++w) wr[w] = Word4<F>::op(wa[w], wb[w]);
+        memcpy(&r, wr, 16);
+      } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+          r.v[e] = apply(f, x_scalar ? xs : a[u].v[e], (F::kArity == 2 && !y_scalar) ? b[u].v[e] : ys);
+      }
       st_stream(op + base + (size_t)u * kThreads, r);
     }
   }

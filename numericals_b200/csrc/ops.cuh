@@ -54,6 +54,30 @@ template <typename T> struct DivOp {
 NUK_CMP_FUNCTOR(LtOp, <) NUK_CMP_FUNCTOR(LeOp, <=) NUK_CMP_FUNCTOR(EqOp, ==)
 NUK_CMP_FUNCTOR(NeqOp, !=) NUK_CMP_FUNCTOR(GeOp, >=) NUK_CMP_FUNCTOR(GtOp, >)
 
+// ---- 8-bit SIMD-in-a-word forms (four elements per instruction group): without them the byte
+// ops are issue-bound at ~45% of the HBM roofline (profiles/sweep_r01_a.jsonl)
+#define NUK_WORD4(FUNCTOR, EXPR)                                                 \
+  template <> struct Word4<FUNCTOR> {                                            \
+    static constexpr bool ok = true;                                             \
+    NUK_D static uint32_t op(uint32_t a, uint32_t b) { return (EXPR); }          \
+  };
+NUK_WORD4(AddOp<int8_t>, __vadd4(a, b))
+NUK_WORD4(SubOp<int8_t>, __vsub4(a, b))
+NUK_WORD4(MaxOp<int8_t>, __vmaxs4(a, b))
+NUK_WORD4(MinOp<int8_t>, __vmins4(a, b))
+NUK_WORD4(MaxOp<uint8_t>, __vmaxu4(a, b))
+NUK_WORD4(MinOp<uint8_t>, __vminu4(a, b))
+NUK_WORD4(LtOp<int8_t>, __vcmplts4(a, b) & 0x01010101u)
+NUK_WORD4(LeOp<int8_t>, __vcmples4(a, b) & 0x01010101u)
+NUK_WORD4(GeOp<int8_t>, __vcmpges4(a, b) & 0x01010101u)
+NUK_WORD4(GtOp<int8_t>, __vcmpgts4(a, b) & 0x01010101u)
+NUK_WORD4(LtOp<uint8_t>, __vcmpltu4(a, b) & 0x01010101u)
+NUK_WORD4(LeOp<uint8_t>, __vcmpleu4(a, b) & 0x01010101u)
+NUK_WORD4(GeOp<uint8_t>, __vcmpgeu4(a, b) & 0x01010101u)
+NUK_WORD4(GtOp<uint8_t>, __vcmpgtu4(a, b) & 0x01010101u)
+NUK_WORD4(EqOp<uint8_t>, __vcmpeq4(a, b) & 0x01010101u)
+NUK_WORD4(NeqOp<uint8_t>, __vcmpne4(a, b) & 0x01010101u)
+
 template <typename T> struct AbsOp {
   using In = T; using Out = T;
   static constexpr int kArity = 1;

@@ -70,6 +70,31 @@ template <typename T> struct MomentsR {  // (sum x, sum x*x) in one pass
   NUK_D static void store(T *o1, T *o2, int64_t i, Acc a) { o1[i] = a.s; o2[i] = a.q; }
 };
 
+// ---- 8/16-bit inputs: accumulate a whole 32-bit word per instruction (dp4a / dp2a for sums, packed
+// SIMD max/min for extrema) instead of extracting bytes; without this the narrow reductions are
+// issue-bound (i8sum 61%, i8hmax 50% of the HBM roofline in profiles/sweep_r01_a.jsonl).
+template <class R> struct WordRed { static constexpr bool ok = false; };
+#define NUK_WORDRED(RED, IDENT, ACC_EXPR, FINISH_BODY)                                          \
+  template <> struct WordRed<RED> {                                                             \
+    static constexpr bool ok = true;                                                            \
+    using A = typename RED::Acc;                                                                \
+    NUK_D static uint32_t identity() { return (IDENT); }                                        \
+    NUK_D static uint32_t acc(uint32_t a, uint32_t w) { return (ACC_EXPR); }                    \
+    NUK_D static A finish(A r, uint32_t a) { FINISH_BODY }                                      \
+  };
+NUK_WORDRED(SumR<int8_t>, 0u, (uint32_t)__dp4a((int)w, 0x01010101, (int)a), return r + a;)
+NUK_WORDRED(SumR<int16_t>, 0u, (uint32_t)__dp2a_lo((int)w, 0x00000101, (int)a), return r + a;)
+#define NUK_UNPACK4(T, OP) for (int k = 0; k < 4; ++k) { const T v = (T)(a >> (8 * k)); r = (v OP r) ? v : r; } return r;
+#define NUK_UNPACK2(T, OP) for (int k = 0; k < 2; ++k) { const T v = (T)(a >> (16 * k)); r = (v OP r) ? v : r; } return r;
+NUK_WORDRED(MaxR<int8_t>, 0x80808080u, __vmaxs4(a, w), NUK_UNPACK4(int8_t, >))
+NUK_WORDRED(MinR<int8_t>, 0x7f7f7f7fu, __vmins4(a, w), NUK_UNPACK4(int8_t, <))
+NUK_WORDRED(MaxR<uint8_t>, 0u, __vmaxu4(a, w), NUK_UNPACK4(uint8_t, >))
+NUK_WORDRED(MinR<uint8_t>, 0xffffffffu, __vminu4(a, w), NUK_UNPACK4(uint8_t, <))
+NUK_WORDRED(MaxR<int16_t>, 0x80008000u, __vmaxs2(a, w), NUK_UNPACK2(int16_t, >))
+NUK_WORDRED(MinR<int16_t>, 0x7fff7fffu, __vmins2(a, w), NUK_UNPACK2(int16_t, <))
+NUK_WORDRED(MaxR<uint16_t>, 0u, __vmaxu2(a, w), NUK_UNPACK2(uint16_t, >))
+NUK_WORDRED(MinR<uint16_t>, 0xffffffffu, __vminu2(a, w), NUK_UNPACK2(uint16_t, <))
+
 template <typename A> NUK_D A shfl_down(A v, int delta) {
   constexpr int W = (sizeof(A) + 3) / 4;
   unsigned w[W];
@@ -117,15 +142,32 @@ k_reduce_flat(size_t n, const typename R::In *x, typename R::Acc *partials, type
   A acc[E];
 #pragma unroll
   for (int e = 0; e < E; ++e) acc[e] = init;
+  uint32_t wacc[4];
+  if constexpr (WordRed<R>::ok) {
+#pragma unroll
+    for (int w = 0; w < 4; ++w) wacc[w] = WordRed<R>::identity();
+  }
   for (size_t t = blockIdx.x; t < nfull; t += gridDim.x) {
     const size_t base = t * kTile + threadIdx.x;
     P v[UNROLL];
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) v[u] = ld_stream(xp + base + (size_t)u * kThreads);
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u)
+    for (int u = 0; u < UNROLL; ++u) {
+      if constexpr (WordRed<R>::ok) {
+        uint32_t w4[4];
+        memcpy(w4, &v[u], 16);
 #pragma unroll
-      for (int e = 0; e < E; ++e) acc[e] = R::combine(acc[e], R::load(v[u].v[e]));
+        for (int w = 0; w < 4; ++w) wacc[w] = WordRed<R>::acc(wacc[w], w4[w]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) acc[e] = R::combine(acc[e], R::load(v[u].v[e]));
+      }
+    }
+  }
+  if constexpr (WordRed<R>::ok) {
+#pragma unroll
+    for (int w = 0; w < 4; ++w) acc[w] = WordRed<R>::finish(acc[w], wacc[w]);
   }
   if (blockIdx.x == nfull % gridDim.x) {
     for (size_t p = nfull * kTile + threadIdx.x; p < npack; p += kThreads) {

@@ -288,6 +288,7 @@ static int argred_typed(long n, const void *x, long ix, long *result) {
 }
 
 int dot_value(int dtype, long n, const void *x, long incx, const void *y, long incy, void *result) {
+  nuk_clear_error();
   switch (dtype) {
     case NUK_F32: return dot_typed<float>(n, x, incx, y, incy, result);
     case NUK_F64: return dot_typed<double>(n, x, incx, y, incy, result);
@@ -317,6 +318,7 @@ template <bool IS_MAX> static int argred_by_type(int dtype, long n, const void *
   return NUK_ERR_UNSUPPORTED;
 }
 int argred_value(int is_max, int dtype, long n, const void *x, long incx, long *result) {
+  nuk_clear_error();
   return is_max ? argred_by_type<true>(dtype, n, x, incx, result) : argred_by_type<false>(dtype, n, x, incx, result);
 }
 

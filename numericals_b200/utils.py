@@ -151,7 +151,7 @@ def asarray(array_like, type=None):
         type = array_like.dtype if isinstance(array_like, np.ndarray) and np.dtype(array_like.dtype) in T._FROM_NP \
             else config.array_element_type
     et = T.normalize(type)
-    h = np.ascontiguousarray(np.asarray(array_like), dtype=T.np_dtype(et))
+    h = np.asarray(array_like, dtype=T.np_dtype(et), order="C")   # (ascontiguousarray would turn rank 0 into rank 1)
     a = empty(h.shape, et)
     if h.size:
         a.copy_from_numpy(h)

@@ -257,7 +257,8 @@ def test_dot_and_arg_reductions(nu, oracle):
         assert call_bmas(_lib.bmas(p + "dot"), n, dx.ptr, 1, dy.ptr, 1) == want
         assert call_bmas(_lib.bmas(p + "dot"), n, x.ctypes.data, 1, y.ctypes.data, 1) == want
     x, y = rnd(rng, np.float64, n, 0, 1), rnd(rng, np.float64, n, 0, 1)
-    got = call_bmas(_lib.bmas("ddot"), n, Dev(nu, x).ptr, 1, Dev(nu, y).ptr, 1)
+    dx, dy = Dev(nu, x), Dev(nu, y)                           # keep the storage alive across the call
+    got = call_bmas(_lib.bmas("ddot"), n, dx.ptr, 1, dy.ptr, 1)
     assert abs(got - float(np.dot(x, y))) < 1e-12 * n
     for p in ALL_PREFIXES:
         dt = np.dtype(NP_OF[p])
