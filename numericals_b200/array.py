@@ -160,7 +160,7 @@ class DenseArray:
         return self.to_numpy().reshape(-1)[0]
 
     def copy_from_numpy(self, a):
-        a = np.ascontiguousarray(a, dtype=T.np_dtype(self.element_type))
+        a = np.asarray(a, dtype=T.np_dtype(self.element_type), order="C")   # keeps rank 0 (ascontiguousarray does not)
         if tuple(a.shape) != self.dimensions or not self.is_contiguous():
             raise ValueError("copy_from_numpy needs a contiguous array of the same shape")
         lib = L.lib()

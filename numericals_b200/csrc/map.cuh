@@ -36,6 +36,13 @@ template <class F> struct PackOf {
   using POut = Pack<Out, E>;
 };
 
+// packs per thread in the flat kernel: 4 unless the functor says otherwise (F::kMapUnroll);
+// exp_f32 runs best with 2 (5.9 vs 5.2 TB/s), log/sin/tanh with 4 (profiles/membench_r01.txt)
+template <class F, class = void> struct MapUnroll { static constexpr int value = 4; };
+template <class F> struct MapUnroll<F, std::void_t<decltype(F::kMapUnroll)>> {
+  static constexpr int value = F::kMapUnroll;
+};
+
 template <class F> NUK_D typename F::Out apply(const F &f, typename F::In a, typename F::In b) {
   if constexpr (F::kArity == 2) return f(a, b);
   else return f(a);
@@ -64,8 +71,11 @@ k_map_flat(size_t n, const typename F::In *x, const typename F::In *y, typename 
   const PIn *yp = reinterpret_cast<const PIn *>(y);
   POut *op = reinterpret_cast<POut *>(out);
 
-  for (size_t t = blockIdx.x; t < nfull; t += gridDim.x) {
-    const size_t base = t * kTile + threadIdx.x;
+  // ONE tile per CTA (grid = nfull + 1): on B200 the hardware CTA scheduler spreads the tiles over
+  // the HBM channels better than a persistent grid-stride loop does -- 6.8 vs 5.9 TB/s for a unary
+  // f32 map, profiles/membench_r01.txt -- so the "grid-stride" loop degenerates to one iteration.
+  if (blockIdx.x < nfull) {
+    const size_t base = (size_t)blockIdx.x * kTile + threadIdx.x;
     PIn a[UNROLL], b[UNROLL];
     if (!x_scalar) {
 #pragma unroll
@@ -96,8 +106,8 @@ k_map_flat(size_t n, const typename F::In *x, const typename F::In *y, typename 
       st_stream(op + base + (size_t)u * kThreads, r);
     }
   }
-  // remainder packs and the element tail: one CTA (the one whose turn it would be)
-  if (blockIdx.x == nfull % gridDim.x) {
+  // remainder packs and the element tail: the last CTA
+  if (blockIdx.x == nfull) {
     for (size_t p = nfull * kTile + threadIdx.x; p < npack; p += kThreads) {
       PIn a, b;
       if (!x_scalar) a = ld_stream(xp + p);
@@ -313,10 +323,14 @@ template <class F> int launch_map(const MapProblem &p, F f = F()) {
     const bool ys = !binary || (y == nullptr) || sy == 0 || p.rank == 0;
     if (so == 1 && (xs || sx == 1) && (ys || sy == 1) && aligned_to(out, sizeof(typename P::POut)) &&
         (xs || vec_ok_in(x, 1)) && (ys || vec_ok_in(y, 1))) {
-      const size_t tiles = n / E / ((size_t)kThreads * UNROLL) + 1;
-      const int grid = grid_for(tiles, (int)option("grid_mult"));
-      k_map_flat<F, UNROLL><<<grid, kThreads, 0, p.stream>>>(n, x, y, out, xs ? 1 : 0, ys ? 1 : 0,
-                                                             p.xv, p.yv, f);
+      constexpr int FU = MapUnroll<F>::value;    // per-functor unroll (profiles/membench_r01.txt)
+      const size_t nfull = n / E / ((size_t)kThreads * FU);
+      if (nfull + 1 > 0x7fffffffu) {
+        set_error(NUK_ERR_INVALID, "array too large for one launch (%zu tiles)", nfull);
+        return NUK_ERR_INVALID;
+      }
+      k_map_flat<F, FU><<<(unsigned)(nfull + 1), kThreads, 0, p.stream>>>(n, x, y, out, xs ? 1 : 0,
+                                                                       ys ? 1 : 0, p.xv, p.yv, f);
       return post_launch("k_map_flat");
     }
   }

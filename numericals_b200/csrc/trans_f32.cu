@@ -7,23 +7,28 @@
 
 namespace nuk {
 
-#define NUK_F32_UNARY(Name, FN)                         \
+#define NUK_F32_UNARY_U(Name, FN, UNR)                  \
   struct Name {                                         \
     using In = float; using Out = float;                \
     static constexpr int kArity = 1;                    \
+    static constexpr int kMapUnroll = UNR;              \
     NUK_D float operator()(float a) const { return nukmath::FN(a); } \
   };
+#define NUK_F32_UNARY(Name, FN) NUK_F32_UNARY_U(Name, FN, 4)
+#define NUK_F32_VIA_F64(Name, FN) NUK_F32_UNARY_U(Name, FN, 1)   /* double-float pair math: keep registers low */
 #define NUK_F32_BINARY(Name, FN)                        \
   struct Name {                                         \
     using In = float; using Out = float;                \
     static constexpr int kArity = 2;                    \
+    static constexpr int kMapUnroll = 1;                \
     NUK_D float operator()(float a, float b) const { return nukmath::FN(a, b); } \
   };
-NUK_F32_UNARY(SinF, sin_f32) NUK_F32_UNARY(CosF, cos_f32) NUK_F32_UNARY(TanF, tan_f32)
-NUK_F32_UNARY(AsinF, asin_f32) NUK_F32_UNARY(AcosF, acos_f32) NUK_F32_UNARY(AtanF, atan_f32)
-NUK_F32_UNARY(SinhF, sinh_f32) NUK_F32_UNARY(CoshF, cosh_f32) NUK_F32_UNARY(TanhF, tanh_f32)
-NUK_F32_UNARY(AsinhF, asinh_f32) NUK_F32_UNARY(AcoshF, acosh_f32) NUK_F32_UNARY(AtanhF, atanh_f32)
-NUK_F32_UNARY(ExpF, exp_f32) NUK_F32_UNARY(LogF, log_f32)
+NUK_F32_UNARY(SinF, sin_f32) NUK_F32_UNARY(CosF, cos_f32) NUK_F32_UNARY(TanhF, tanh_f32)
+NUK_F32_UNARY(LogF, log_f32)
+NUK_F32_UNARY_U(ExpF, exp_f32, 2)   // 5.9 TB/s with 2 packs per thread vs 5.2 with 4 (profiles/membench_r01.txt)
+NUK_F32_VIA_F64(TanF, tan_f32) NUK_F32_VIA_F64(AsinF, asin_f32) NUK_F32_VIA_F64(AcosF, acos_f32)
+NUK_F32_VIA_F64(AtanF, atan_f32) NUK_F32_VIA_F64(SinhF, sinh_f32) NUK_F32_VIA_F64(CoshF, cosh_f32)
+NUK_F32_VIA_F64(AsinhF, asinh_f32) NUK_F32_VIA_F64(AcoshF, acosh_f32) NUK_F32_VIA_F64(AtanhF, atanh_f32)
 NUK_F32_BINARY(PowF, pow_f32) NUK_F32_BINARY(Atan2F, atan2_f32)
 
 int launch_trans_f32(int op, int arity, const MapProblem &p) {

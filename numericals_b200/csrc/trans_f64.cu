@@ -8,12 +8,14 @@ namespace nuk {
   struct Name {                                         \
     using In = double; using Out = double;              \
     static constexpr int kArity = 1;                    \
+    static constexpr int kMapUnroll = 2;                \
     NUK_D double operator()(double a) const { return nukmath::FN(a); } \
   };
 #define NUK_F64_BINARY(Name, FN)                        \
   struct Name {                                         \
     using In = double; using Out = double;              \
     static constexpr int kArity = 2;                    \
+    static constexpr int kMapUnroll = 1;                \
     NUK_D double operator()(double a, double b) const { return nukmath::FN(a, b); } \
   };
 NUK_F64_UNARY(SinD, sin_f64) NUK_F64_UNARY(CosD, cos_f64) NUK_F64_UNARY(TanD, tan_f64)

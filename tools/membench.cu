@@ -100,6 +100,26 @@ __global__ void __launch_bounds__(THREADS) kread(size_t nvec, const float4 *x, f
   if (s == 12345.678f) o[0] = s;
 }
 
+// transcendental maps from the product header, one tile per CTA: (threads, unroll) probe
+#include "../numericals_b200/csrc/nukmath_f32.cuh"
+struct FExp { __device__ static float f(float x) { return nukmath::exp_f32(x); } static const char *name() { return "exp"; } };
+struct FLog { __device__ static float f(float x) { return nukmath::log_f32(x); } static const char *name() { return "log"; } };
+struct FSin { __device__ static float f(float x) { return nukmath::sin_f32(x); } static const char *name() { return "sin"; } };
+struct FTanh { __device__ static float f(float x) { return nukmath::tanh_f32(x); } static const char *name() { return "tanh"; } };
+template <class F, int UNROLL, int THREADS>
+__global__ void __launch_bounds__(THREADS) kfun(size_t nvec, const float4 *x, float4 *o) {
+  const size_t base = (size_t)blockIdx.x * THREADS * UNROLL + threadIdx.x;
+  float4 a[UNROLL];
+#pragma unroll
+  for (int u = 0; u < UNROLL; ++u) a[u] = ld128<P_CS>(x + base + (size_t)u * THREADS);
+#pragma unroll
+  for (int u = 0; u < UNROLL; ++u) {
+    float4 r;
+    r.x = F::f(a[u].x); r.y = F::f(a[u].y); r.z = F::f(a[u].z); r.w = F::f(a[u].w);
+    st128<P_CS>(o + base + (size_t)u * THREADS, r);
+  }
+}
+
 static float *X, *Y, *O;
 static size_t N;
 static cudaEvent_t e0, e1;
@@ -144,6 +164,22 @@ template <int ARITY, int LPOL, int SPOL, int UNROLL, int THREADS> static void be
   report(name, ARITY, run([&] { k256<ARITY, LPOL, SPOL, UNROLL, THREADS><<<grid, THREADS>>>(nvec, (const f8 *)X, (const f8 *)Y, (f8 *)O); }));
 }
 
+template <class F, int UNROLL, int THREADS> static void benchfun() {
+  const size_t nvec = N / 4, tile = (size_t)THREADS * UNROLL;
+  char name[128];
+  snprintf(name, sizeof(name), "%s f32 one tile per CTA unroll%d thr%d", F::name(), UNROLL, THREADS);
+  report(name, 1, run([&] { kfun<F, UNROLL, THREADS><<<(unsigned)(nvec / tile), THREADS>>>(nvec, (const float4 *)X, (float4 *)O); }));
+}
+template <class F> static void benchfun_all() {
+  benchfun<F, 1, 128>(); benchfun<F, 2, 128>(); benchfun<F, 4, 128>();
+  benchfun<F, 1, 256>(); benchfun<F, 2, 256>(); benchfun<F, 4, 256>();
+  benchfun<F, 1, 512>(); benchfun<F, 2, 512>(); benchfun<F, 1, 1024>();
+}
+__global__ void kinit(size_t n, float *x) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    x[i] = 1e-3f + (float)((i * 2654435761ull) & 0xffffff) * (0.998f / 16777216.0f);   // U[1e-3, 1)
+}
+
 int main(int argc, char **argv) {
   N = (size_t)1 << (argc > 1 ? atoi(argv[1]) : 28);
   cudaDeviceProp p;
@@ -151,7 +187,14 @@ int main(int argc, char **argv) {
   SMS = p.multiProcessorCount;
   printf("device %s, %d SMs, N = %zu f32 (%.0f MiB per array)\n", p.name, SMS, N, N * 4.0 / (1 << 20));
   CK(cudaMalloc(&X, N * 4)); CK(cudaMalloc(&Y, N * 4)); CK(cudaMalloc(&O, N * 4));
-  CK(cudaMemset(X, 0, N * 4)); CK(cudaMemset(Y, 0, N * 4));
+  kinit<<<148 * 8, 256>>>(N, X);
+  kinit<<<148 * 8, 256>>>(N, Y);
+  CK(cudaDeviceSynchronize());
+  if (argc > 2) {  // "fun": only the transcendental (threads, unroll) probe
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    benchfun_all<FExp>(); benchfun_all<FLog>(); benchfun_all<FSin>(); benchfun_all<FTanh>();
+    return 0;
+  }
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   report("cudaMemcpyAsync D2D", 1, run([&] { CK(cudaMemcpyAsync(O, X, N * 4, cudaMemcpyDeviceToDevice)); }));
   report("cudaMemsetAsync (write only; GB/s counts 2x)", 1, run([&] { CK(cudaMemsetAsync(O, 1, N * 4)); }));
