@@ -1,0 +1,45 @@
+"""CPU: the product math headers compiled for the host, swept against a higher-precision truth and
+against SLEEF u10 (tests/ulp/ulp_sweep.cpp).  Pass criterion: max error < 1 ULP (faithful) AND
+integer ULP distance to SLEEF u10 <= 1 wherever SLEEF is inside its own bound -- the north-star
+tolerance.  The full 2^32-input exhaustive runs are recorded in profiles/ulp_report_r01.jsonl
+(tools: `ulp_sweep <fn> f32`); here a 2^27-input window per function keeps the suite fast, and the
+GPU tests prove the device executes these same expressions bit for bit."""
+import json
+import subprocess
+
+import pytest
+
+from _helpers import build_host_tool
+
+F32 = ["exp", "log", "sin", "cos", "tanh", "tan", "asin", "acos", "atan", "sinh", "cosh", "asinh", "acosh", "atanh"]
+F64 = F32
+
+
+@pytest.fixture(scope="module")
+def sweep():
+    return build_host_tool("ulp_sweep.cpp", "ulp_sweep")
+
+
+@pytest.mark.parametrize("fn", F32)
+def test_f32_window(fn, sweep):
+    # bit patterns 0x3c000000..0x44000000: |x| in [2^-7, 512) positive -- dense where the functions live
+    out = subprocess.check_output([sweep, fn, "f32", "0x3c000000", "0x44000000"]).decode()
+    r = json.loads(out.strip().splitlines()[-1])
+    assert r["max_ulp"] < 1.0, r
+    assert r["max_ulp_dist_vs_sleef_u10"] <= 1, r
+
+
+@pytest.mark.parametrize("fn", F64)
+def test_f64_samples(fn, sweep):
+    out = subprocess.check_output([sweep, fn, "f64", "4000000"]).decode()
+    r = json.loads(out.strip().splitlines()[-1])
+    assert r["max_ulp"] < 1.0, r
+    assert r["max_ulp_dist_vs_sleef_u10"] <= 1, r
+
+
+@pytest.mark.parametrize("fn,typ", [("pow", "f64"), ("atan2", "f64"), ("pow", "f32b"), ("atan2", "f32b")])
+def test_binary_samples(fn, typ, sweep):
+    out = subprocess.check_output([sweep, fn, typ, "4000000"]).decode()
+    r = json.loads(out.strip().splitlines()[-1])
+    assert r["max_ulp"] < 1.0, r
+    assert r["max_ulp_dist_vs_sleef_u10"] <= 1, r
