@@ -161,7 +161,7 @@ def cpu_baseline(sample_elems, reps, threads):
     }
 
 
-def run_reference(args):
+def run_reference(args, emit):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -194,7 +194,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "Gelem/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -209,8 +209,18 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--e2e-steps", type=int, default=2)
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL's version banner)
+    # are sent to stderr for the duration of the run; emit() writes to the saved descriptor.
+    sys.stdout.flush()
+    saved_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(saved_fd, (json.dumps(obj) + "\n").encode())
+
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, emit)
     args.warmup = max(args.warmup, 3)
 
     import torch
@@ -369,7 +379,7 @@ def main():
             "hbm_gbs": value * 8.0, "per_ufunc": per_ufunc, "roofline": roofline, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks, "cpu_baseline": cpu, "extra": extra,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0

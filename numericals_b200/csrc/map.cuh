@@ -74,7 +74,34 @@ k_map_flat(size_t n, const typename F::In *x, const typename F::In *y, typename 
   // ONE tile per CTA (grid = nfull + 1): on B200 the hardware CTA scheduler spreads the tiles over
   // the HBM channels better than a persistent grid-stride loop does -- 6.8 vs 5.9 TB/s for a unary
   // f32 map, profiles/membench_r01.txt -- so the "grid-stride" loop degenerates to one iteration.
-  if (blockIdx.x < nfull) {
+  if (blockIdx.x < nfull && !x_scalar && (F::kArity == 1 || !y_scalar)) {
+    // all-vector tile (the hot case): no per-element scalar selects
+    const size_t base = (size_t)blockIdx.x * kTile + threadIdx.x;
+    PIn a[UNROLL], b[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) a[u] = ld_stream(xp + base + (size_t)u * kThreads);
+    if (F::kArity == 2) {
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) b[u] = ld_stream(yp + base + (size_t)u * kThreads);
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      POut r;
+      if constexpr (Word4<F>::ok) {
+        uint32_t wa[4], wb[4], wr[4];
+        memcpy(wa, &a[u], 16);
+        memcpy(wb, &b[u], 16);
+#pragma unroll
+        for (int w = 0; w < 4; ++w) wr[w] = Word4<F>::op(wa[w], wb[w]);
+        memcpy(&r, wr, 16);
+      } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) r.v[e] = apply(f, a[u].v[e], F::kArity == 2 ? b[u].v[e] : In());
+      }
+      st_stream(op + base + (size_t)u * kThreads, r);
+    }
+  } else if (blockIdx.x < nfull) {
+    // a scalar operand (uniform across the grid): same tile with broadcast values
     const size_t base = (size_t)blockIdx.x * kTile + threadIdx.x;
     PIn a[UNROLL], b[UNROLL];
     if (!x_scalar) {
