@@ -78,6 +78,24 @@ def test_unary(name, dt, nu, oracle):
     assert np.array_equal(np.isnan(got), np.isnan(truth)), name
 
 
+@pytest.mark.parametrize("name", ["exp", "sin", "log", "tanh", "cos"])
+def test_c2_functions_dense_bit_patterns(name, nu):
+    """EVERY single-float in [2^-7, 8) and its negative (2 x 83.9M bit patterns): the device result
+    equals the host compile of the same header bit for bit.  This is the bridge from the exhaustive
+    CPU ULP sweeps to the GPU code (it also covers the MUFU.RCP-seeded reciprocal inside tanh,
+    which the host replaces by a correctly rounded division)."""
+    lo, hi = 0x3C000000, 0x41000000
+    step = 1 << 24
+    for sign in (0, 0x80000000):
+        if name == "log" and sign:
+            continue
+        for b0 in range(lo, hi, step):
+            x = (np.arange(b0, b0 + step, dtype=np.uint32) | np.uint32(sign)).view(np.float32)
+            got = device_unary(nu, name, x)
+            host = host_unary(name, x)
+            assert got.tobytes() == host.tobytes(), (name, hex(b0), int((got != host).sum()))
+
+
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 def test_pow_atan2(dt, nu, oracle):
     from numericals_b200 import _lib
