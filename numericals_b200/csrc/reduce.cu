@@ -16,6 +16,7 @@
 //                   and walk the rows IN ORDER (== the reference's row-accumulate order);
 //                   rows may be split into chunks whose partials are combined in order
 //   k_reduce_any  : anything else, one thread per output
+#include <cuda.h>   // CUtensorMap types only; the encoder is fetched with cudaGetDriverEntryPoint
 #include <cfloat>
 #include <limits>
 #include "dispatch.cuh"
@@ -388,6 +389,196 @@ k_reduce_cols(AxisDesc d, int64_t ncols, int64_t nouter, int chunks, int64_t row
   }
 }
 
+// ------------------------------------------------------------------ sequential column walk, TMA-fed
+// The reference's axis-0 order (out <- out + row_i, i = 0..n-1; sum.lisp:69-71) makes every column
+// a strictly sequential chain, so the only parallelism is ACROSS columns: 16384 columns = 128 CTAs
+// of 128 threads, far too few loads in flight for HBM with ordinary ld.global (0.9 TB/s measured).
+// Here one elected thread streams the CTA's 128-column slab through a ring of shared-memory stages
+// with 1-D bulk async copies (cp.async.bulk, the TMA engine, completion on an mbarrier), 128 KB in
+// flight per SM, while the 128 threads fold the rows of each landed stage IN ORDER.  Result: bit-
+// identical to the reference order at the HBM roofline.
+NUK_D uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+NUK_D void mbar_init(uint64_t *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+NUK_D void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+NUK_D void bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+NUK_D bool mbar_try_wait(uint64_t *bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
+constexpr int kSeqThreads = 128;  // columns per CTA
+constexpr int kSeqRows = 16;      // rows per stage
+constexpr int kSeqStages = 8;     // stages in flight
+
+template <class R>
+__global__ void __launch_bounds__(kSeqThreads)
+k_reduce_cols_seq(AxisDesc d, int64_t ncols, const typename R::In *x, typename R::In *o1,
+                  typename R::In *o2, typename R::Acc init) {
+  using T = typename R::In;
+  using A = typename R::Acc;
+  extern __shared__ __align__(128) unsigned char seq_smem[];
+  T *buf = reinterpret_cast<T *>(seq_smem);  // [kSeqStages][kSeqRows][kSeqThreads]
+  __shared__ __align__(8) uint64_t full[kSeqStages];
+
+  const int tid = threadIdx.x;
+  const int64_t c0 = (int64_t)blockIdx.x * kSeqThreads;
+  const int ncol_here = (int)((ncols - c0 < kSeqThreads) ? (ncols - c0) : kSeqThreads);
+  int64_t ox = 0, oo = 0;
+  {
+    AxisDesc outer = d;
+    outer.orank = d.orank - 1;
+    out_offsets(outer, (int64_t)blockIdx.y, &ox, &oo);
+  }
+  const T *base = x + ox + c0;
+  const unsigned seg_bytes = (unsigned)(ncol_here * sizeof(T));
+  const int64_t nstages = (d.rlen + kSeqRows - 1) / kSeqRows;
+
+  if (tid == 0) {
+    for (int s = 0; s < kSeqStages; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // warp 0 fills slot it % kSeqStages with stage `it`: lane 0 arms the barrier with the byte count,
+  // then lane r issues the bulk copy of row r (one UBLKCP per lane, so the 16 row copies of a
+  // stage are issued together instead of serially by one thread)
+  auto issue = [&](int64_t it) {
+    const int slot = (int)(it % kSeqStages);
+    const int64_t r0 = it * kSeqRows;
+    const int nr = (int)((d.rlen - r0 < kSeqRows) ? (d.rlen - r0) : kSeqRows);
+    if (tid == 0) mbar_expect_tx(&full[slot], (unsigned)nr * seg_bytes);
+    __syncwarp();
+    if (tid < nr)
+      bulk_g2s(buf + ((size_t)slot * kSeqRows + tid) * kSeqThreads, base + (r0 + tid) * d.rstride, seg_bytes,
+               &full[slot]);
+  };
+  if (tid < 32)
+    for (int64_t it = 0; it < kSeqStages && it < nstages; ++it) issue(it);
+
+  A acc = init;
+  for (int64_t it = 0; it < nstages; ++it) {
+    const int slot = (int)(it % kSeqStages);
+    const unsigned parity = (unsigned)((it / kSeqStages) & 1);
+    while (!mbar_try_wait(&full[slot], parity)) {
+    }
+    const int64_t r0 = it * kSeqRows;
+    const int nr = (int)((d.rlen - r0 < kSeqRows) ? (d.rlen - r0) : kSeqRows);
+    if (tid < ncol_here) {
+      const T *col = buf + (size_t)slot * kSeqRows * kSeqThreads + tid;
+      if (nr == kSeqRows) {
+        T v[kSeqRows];
+#pragma unroll
+        for (int r = 0; r < kSeqRows; ++r) v[r] = col[r * kSeqThreads];
+#pragma unroll
+        for (int r = 0; r < kSeqRows; ++r) acc = R::combine(acc, R::load(v[r]));   // rows in order
+      } else {
+        for (int r = 0; r < nr; ++r) acc = R::combine(acc, R::load(col[r * kSeqThreads]));
+      }
+    }
+    __syncthreads();  // every thread is done reading the slot before it is refilled
+    if (tid < 32 && it + kSeqStages < nstages) issue(it + kSeqStages);
+  }
+  if (tid < ncol_here) R::store(o1, o2, oo + (c0 + tid) * d.oos[d.orank - 1], acc);
+}
+
+// Same walk fed by ONE tensor-map TMA request per stage (cp.async.bulk.tensor, a 128-column x
+// 16-row box = 16 KB for doubles) instead of 16 one-row bulk copies: the per-request cost of the
+// TMA engine is what limited the 1-D version (2.9 TB/s).  Tensor: (columns, rows, outer) with byte
+// strides; out-of-bounds parts of a box are zero-filled and still counted, so every stage expects
+// the full box.
+template <class R>
+__global__ void __launch_bounds__(kSeqThreads)
+k_reduce_cols_tma(const __grid_constant__ CUtensorMap tmap, AxisDesc d, int64_t ncols,
+                  typename R::In *o1, typename R::In *o2, typename R::Acc init) {
+  using T = typename R::In;
+  using A = typename R::Acc;
+  extern __shared__ __align__(128) unsigned char seq_smem[];
+  T *buf = reinterpret_cast<T *>(seq_smem);  // [kSeqStages][kSeqRows][kSeqThreads]
+  __shared__ __align__(8) uint64_t full[kSeqStages];
+  const int tid = threadIdx.x;
+  const int64_t c0 = (int64_t)blockIdx.x * kSeqThreads;
+  const int ncol_here = (int)((ncols - c0 < kSeqThreads) ? (ncols - c0) : kSeqThreads);
+  const int outer = (int)blockIdx.y;
+  const int64_t oo = d.orank >= 2 ? (int64_t)outer * d.oos[0] : 0;
+  const int64_t nstages = (d.rlen + kSeqRows - 1) / kSeqRows;
+  constexpr unsigned kBoxBytes = kSeqRows * kSeqThreads * sizeof(T);
+
+  if (tid == 0) {
+    for (int s = 0; s < kSeqStages; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int64_t it) {  // thread 0
+    const int slot = (int)(it % kSeqStages);
+    mbar_expect_tx(&full[slot], kBoxBytes);
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(buf + (size_t)slot * kSeqRows * kSeqThreads)),
+        "l"(&tmap), "r"((int)c0), "r"((int)(it * kSeqRows)), "r"(outer), "r"(smem_u32(&full[slot]))
+        : "memory");
+  };
+  if (tid == 0)
+    for (int64_t it = 0; it < kSeqStages && it < nstages; ++it) issue(it);
+
+  A acc = init;
+  for (int64_t it = 0; it < nstages; ++it) {
+    const int slot = (int)(it % kSeqStages);
+    const unsigned parity = (unsigned)((it / kSeqStages) & 1);
+    while (!mbar_try_wait(&full[slot], parity)) {
+    }
+    const int64_t r0 = it * kSeqRows;
+    const int nr = (int)((d.rlen - r0 < kSeqRows) ? (d.rlen - r0) : kSeqRows);
+    if (tid < ncol_here) {
+      const T *col = buf + (size_t)slot * kSeqRows * kSeqThreads + tid;
+      if (nr == kSeqRows) {
+        T v[kSeqRows];
+#pragma unroll
+        for (int r = 0; r < kSeqRows; ++r) v[r] = col[r * kSeqThreads];
+#pragma unroll
+        for (int r = 0; r < kSeqRows; ++r) acc = R::combine(acc, R::load(v[r]));   // rows in order
+      } else {
+        for (int r = 0; r < nr; ++r) acc = R::combine(acc, R::load(col[r * kSeqThreads]));
+      }
+    }
+    __syncthreads();
+    if (tid == 0 && it + kSeqStages < nstages) issue(it + kSeqStages);
+  }
+  if (tid < ncol_here) R::store(o1, o2, oo + (c0 + tid) * d.oos[d.orank - 1], acc);
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (libnuk does not link libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      p = nullptr;
+    }
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
 // fallback: one thread per output, rows in order
 template <class R>
 __global__ void __launch_bounds__(kThreads)
@@ -509,6 +700,52 @@ template <class R> static int run_axis(const ReduceProblem &p, typename R::Acc i
     const int64_t nouter = d.nout / ncols;
     bool vec = aligned_to(x, 16) && (d.rstride % E == 0) && (ncols % E == 0);
     for (int a = 0; a + 1 < d.orank; ++a) vec = vec && (d.oxs[a] % E == 0);
+    // TMA-fed sequential walk: reference order (bit-exact) at HBM speed.  Needs 16-byte aligned row
+    // segments; chosen whenever it covers most of the chip, or when the caller asks for the
+    // reference order.
+    {
+      const int64_t seq_tiles = (ncols + kSeqThreads - 1) / kSeqThreads;
+      bool ok = sizeof(T) >= 4 && aligned_to(x, 16) && ((d.rstride * (int64_t)sizeof(T)) % 16 == 0) &&
+                ((ncols * (int64_t)sizeof(T)) % 16 == 0) && d.rlen >= 4 * kSeqRows && nouter <= 65535;
+      for (int a = 0; a + 1 < d.orank; ++a) ok = ok && ((d.oxs[a] * (int64_t)sizeof(T)) % 16 == 0);
+      const bool covers = seq_tiles * nouter * 4 >= (int64_t)dev->sm_count * 3;   // >= 75% of the SMs
+      if (ok && (covers || (p.flags & NUK_REDUCE_REF_ORDER)) && option("seq_cols") != 0) {
+        const size_t smem = (size_t)kSeqStages * kSeqRows * kSeqThreads * sizeof(T);
+        static bool attr_set = false;   // per template instantiation
+        if (!attr_set) {
+          NUK_CUDA(cudaFuncSetAttribute(k_reduce_cols_seq<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem));
+          attr_set = true;
+        }
+        dim3 grid((unsigned)seq_tiles, (unsigned)nouter);
+        // preferred: one tensor-map TMA request per stage
+        EncodeTiledFn enc = encode_tiled_fn();
+        if (enc && d.orank <= 2 && d.rstride > 0 && (d.orank < 2 || d.oxs[0] > 0) && option("seq_cols") != 2) {
+          CUtensorMap tmap;
+          const cuuint64_t gdim[3] = {(cuuint64_t)ncols, (cuuint64_t)d.rlen, (cuuint64_t)nouter};
+          const cuuint64_t outer_stride = d.orank == 2 ? (cuuint64_t)d.oxs[0] : (cuuint64_t)(d.rlen * d.rstride);
+          const cuuint64_t gstr[2] = {(cuuint64_t)d.rstride * sizeof(T), outer_stride * sizeof(T)};
+          const cuuint32_t box[3] = {(cuuint32_t)kSeqThreads, (cuuint32_t)kSeqRows, 1u};
+          const cuuint32_t estr[3] = {1u, 1u, 1u};
+          const CUresult r = enc(&tmap, sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : CU_TENSOR_MAP_DATA_TYPE_UINT32,
+                                 3, const_cast<T *>(x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+          if (r == CUDA_SUCCESS) {
+            static bool attr2_set = false;
+            if (!attr2_set) {
+              NUK_CUDA(cudaFuncSetAttribute(k_reduce_cols_tma<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)smem));
+              attr2_set = true;
+            }
+            k_reduce_cols_tma<R><<<grid, kSeqThreads, smem, p.stream>>>(tmap, d, ncols, o1, o2, init);
+            return post_launch("k_reduce_cols_tma");
+          }
+        }
+        k_reduce_cols_seq<R><<<grid, kSeqThreads, smem, p.stream>>>(d, ncols, x, o1, o2, init);
+        return post_launch("k_reduce_cols_seq");
+      }
+    }
     const int64_t cols_per_cta = (int64_t)kThreads * (vec ? E : 1);
     const int64_t col_tiles = (ncols + cols_per_cta - 1) / cols_per_cta;
     int chunks = 1;

@@ -102,7 +102,9 @@ static std::unordered_map<std::string, long> &options() {
     m["stage_mb"] = 32;        // chunk size of the host-pointer staging pipeline
     m["stage_slots"] = 3;
     m["col_split_rows"] = 256; // rows per CTA in the split column reduction
-    const char *names[] = {"grid_mult", "reduce_grid_mult", "stage_mb", "stage_slots", "col_split_rows"};
+    m["seq_cols"] = 1;         // 1: TMA-fed sequential (reference-order) column reduction where it fits
+    const char *names[] = {"grid_mult", "reduce_grid_mult", "stage_mb", "stage_slots", "col_split_rows",
+                           "seq_cols"};
     for (const char *n : names) {
       std::string env = "NUK_";
       for (const char *c = n; *c; ++c) env.push_back((char)toupper(*c));

@@ -63,6 +63,27 @@ def test_axis0_sum_is_reference_order_bit_exact(nu, refnu):
             assert fast.tobytes() == nu.sum(nu.asarray(h), axes=0).to_numpy().tobytes(), "not deterministic"
 
 
+def test_wide_axis0_default_is_reference_order_at_speed(nu, refnu):
+    """Wide matrices (>= 75% of the SMs get a 128-column slab) take the TMA-fed sequential column
+    kernel BY DEFAULT: the plain nu:sum / nu:maximum / nu:mean / nu:variance along axis 0 is then
+    bit-identical to the reference's row-accumulate decomposition (out-size >= n branch)."""
+    rng = np.random.default_rng(45)
+    for dt, ncols in ((np.float64, 16384), (np.float32, 16388), (np.float64, 14210)):
+        h = rnd(rng, dt, (300, ncols), -1, 1)
+        x = nu.asarray(h)
+        assert nu.sum(x, axes=0).to_numpy().tobytes() == refnu.reduce("sum", h, 0).tobytes(), (dt, ncols)
+        assert nu.maximum(x, axes=0).to_numpy().tobytes() == refnu.reduce("maximum", h, 0).tobytes()
+        assert nu.minimum(x, axes=0).to_numpy().tobytes() == refnu.reduce("minimum", h, 0).tobytes()
+        assert nu.mean(x, axes=0).to_numpy().tobytes() == refnu.mean(h, 0).tobytes()
+        assert nu.variance(x, axes=0).to_numpy().tobytes() == refnu.variance(h, 0).tobytes()
+        # 3-d: reduce the middle axis of (4, 70, 4096): outer index on grid.y
+    h = rnd(rng, np.float64, (4, 70, 4096), 0, 1)
+    assert nu.sum(nu.asarray(h), axes=1).to_numpy().tobytes() == refnu.reduce("sum", h, 1).tobytes()
+    hi = rnd(rng, np.int32, (200, 16384))
+    with np.errstate(over="ignore"):
+        assert np.array_equal(nu.sum(nu.asarray(hi), axes=0).to_numpy(), hi.sum(axis=0, dtype=np.int32))
+
+
 @pytest.mark.parametrize("prefix", ["i64", "i32", "i16", "i8", "u64", "u32", "u16", "u8"])
 def test_integer_reductions_exact_any_axis(prefix, nu, refnu):
     rng = np.random.default_rng(42)
