@@ -175,6 +175,11 @@ int nuk_fill(int dtype, int rank, const int64_t *dims, const int64_t *so,
 int nuk_reduce(int red, int dtype, int rank, const int64_t *dims, const int64_t *sx,
                int axis, const int64_t *so, const void *x, void *out, int flags,
                nuk_stream_t s);
+/* nu:arg-maximum / nu:arg-minimum along `axis` (src/basic-math/arg-maximum.lisp:31-73): out is
+ * int64, so[] its element strides for the dims of x with `axis` removed; index of the FIRST
+ * extremum.  (The full, flattened form is BMAS_<t>himax / himin.) */
+int nuk_argreduce(int is_max, int dtype, int rank, const int64_t *dims, const int64_t *sx, int axis,
+                  const int64_t *so, const void *x, int64_t *out, nuk_stream_t s);
 /* out[i] = out[i] / divisor, true IEEE division by a stride-0 scalar: the tail of
  * nu:mean (src/statistics/mean.lisp:90-97).  Float dtypes only. */
 int nuk_div_scalar_inplace(int dtype, int64_t n, void *out, double divisor, nuk_stream_t s);

@@ -22,6 +22,7 @@ from .dtypes import (ELEMENT_TYPES, NoCFunction, c_name, c_size, max_type, type_
 from .utils import (IncompatibleBroadcastDimensions, array_equal, asarray, broadcast_compatible_p,  # noqa: F401
                     config, empty, empty_like, fill, full, ones, ones_like, rand, shape,
                     strides_for_broadcast, zeros, zeros_like)
+from .basic_math import arg_maximum, arg_minimum, vdot  # noqa: F401
 from .basic_math import (abs, abs_, add, add_, astype, copy, divide, divide_, eq, fceiling, fceiling_,  # noqa: F401
                          ffloor, ffloor_, fround, fround_, ftruncate, ftruncate_, ge, gt, le, logandc1,
                          lognot, lt, max, maximum, min, minimum, minus, multiply, multiply_, ne, plus,

@@ -343,6 +343,66 @@ def minimum(array_like, out=None, axes=None, keep_dims=False):
     return _reduction("minimum", array_like, out, axes, keep_dims)
 
 
+def _arg_reduction(is_max, array_like, out, axis, keep_dims):
+    """nu:arg-maximum / nu:arg-minimum (src/basic-math/arg-maximum.lisp:31-155): :axis nil gives the
+    row-major index of the extremum of the whole array (a scalar); an integer :axis gives an
+    (signed-byte 64) array of indices along that axis.  Ties: the FIRST index."""
+    lib = L.lib()
+    x = _as_array(array_like)
+    name = "maximum" if is_max else "minimum"
+    T.c_name(x.element_type, name)
+    if axis is None:
+        xc = x if x.is_contiguous() else copy(x)
+        sym = T.prefix(x.element_type) + ("himax" if is_max else "himin")
+        r = int(L.bmas(sym)(C.c_long(xc.total_size), _vp(xc.ptr), C.c_long(1)))
+        if L.last_status() != 0:
+            raise L.NukError(L.last_status(), lib.nuk_last_error().decode())
+        if keep_dims:
+            from .utils import full
+            return full((1,) * x.rank, value=r, type="(signed-byte 64)")
+        return r
+    oshape = _out_shape(x.dimensions, axis, keep_dims)
+    if out is None:
+        out = empty(oshape, "(signed-byte 64)")
+    elif out.dimensions != oshape or out.element_type != "(signed-byte 64)":
+        raise ValueError("arg-%s of dimensions %s on axis %d requires a (signed-byte 64) array of dimensions %s"
+                         % (name, x.dimensions, axis, oshape))
+    ostr = list(out.strides)
+    if keep_dims:
+        del ostr[axis]
+    L.check(lib.nuk_argreduce(1 if is_max else 0, x.dtype_code, x.rank, L.i64_array(x.dimensions),
+                              L.i64_array(x.strides), axis, L.i64_array(ostr), _vp(x.ptr), _vp(out.ptr), _stream()))
+    return out
+
+
+def arg_maximum(array_like, out=None, axis=None, keep_dims=False):
+    """nu:arg-maximum"""
+    return _arg_reduction(True, array_like, out, axis, keep_dims)
+
+
+def arg_minimum(array_like, out=None, axis=None, keep_dims=False):
+    """nu:arg-minimum"""
+    return _arg_reduction(False, array_like, out, axis, keep_dims)
+
+
+def vdot(a, b):
+    """nu:vdot (src/linalg/vdot.lisp:15-25): both arrays as 1-D vectors; multiply + sum fused in one
+    pass (BMAS_<t>dot) instead of the reference's per-row calls accumulated in Lisp."""
+    x, y = _as_array(a), _as_array(b)
+    if x.element_type != y.element_type or x.total_size != y.total_size:
+        raise ValueError("vdot needs two arrays of the same element type and size")
+    xc = x if x.is_contiguous() else copy(x)
+    yc = y if y.is_contiguous() else copy(y)
+    et = x.element_type
+    p = T.prefix(et)
+    if p.startswith("u"):
+        p = "i" + p[1:]           # unsigned arrays use the signed symbol, like add/sum
+    r = L.bmas(p + "dot")(C.c_long(xc.total_size), _vp(xc.ptr), C.c_long(1), _vp(yc.ptr), C.c_long(1))
+    if L.last_status() != 0:
+        raise L.NukError(L.last_status(), L.lib().nuk_last_error().decode())
+    return T.np_dtype(et).type(r)
+
+
 # --------------------------------------------------------------------------- n-ary sugar
 def _nary_type(args, out):
     """n-ary dtype: OUT's type, else max-type over the array arguments and the default element

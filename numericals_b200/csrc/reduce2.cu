@@ -323,3 +323,94 @@ int argred_value(int is_max, int dtype, long n, const void *x, long incx, long *
 }
 
 }  // namespace nuk
+
+// ------------------------------------------------------------------ nd arg-reduction along one axis
+// nu:arg-maximum / nu:arg-minimum with :axis (src/basic-math/arg-maximum.lisp:31-73): per output
+// element the index of the FIRST extremum along `axis`, as (signed-byte 64).  One warp per output,
+// lanes stride over the axis, (value, index) pairs folded by shuffles with the first-index rule.
+namespace nuk {
+struct ArgAxisDesc {
+  int orank;
+  int64_t odims[NUK_MAX_RANK], oxs[NUK_MAX_RANK], oos[NUK_MAX_RANK];
+  int64_t nout, rlen, rstride;
+};
+template <typename T, bool IS_MAX>
+__global__ void __launch_bounds__(kThreads)
+k_argred_axis(ArgAxisDesc d, const T *x, int64_t *out, T init) {
+  using A = ValIdx<T>;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int64_t j = (int64_t)blockIdx.x * (kThreads / 32) + warp;
+  if (j >= d.nout) return;
+  int64_t ox = 0, oo = 0;
+  for (int a = d.orank - 1; a >= 0; --a) {
+    const int64_t q = j / d.odims[a], k = j - q * d.odims[a];
+    ox += k * d.oxs[a];
+    oo += k * d.oos[a];
+    j = q;
+  }
+  auto comb = [](A a, A b) {
+    const bool better = IS_MAX ? (b.v > a.v) : (b.v < a.v);
+    const bool tie_first = (b.v == a.v) && (b.i < a.i);
+    return (better || tie_first) ? b : a;
+  };
+  A acc{init, INT64_MAX};
+  for (int64_t r = lane; r < d.rlen; r += 32) acc = comb(acc, A{x[ox + r * d.rstride], r});
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) acc = comb(acc, shfl_down_any(acc, s));
+  if (lane == 0) out[oo] = acc.i == INT64_MAX ? 0 : acc.i;
+}
+template <typename T, bool IS_MAX> static int argaxis_launch(const ArgAxisDesc &d, const void *x, int64_t *out, cudaStream_t st) {
+  T init;
+  if (std::is_floating_point<T>::value)
+    init = IS_MAX ? -std::numeric_limits<T>::infinity() : std::numeric_limits<T>::infinity();
+  else
+    init = IS_MAX ? std::numeric_limits<T>::lowest() : std::numeric_limits<T>::max();
+  const unsigned grid = (unsigned)((d.nout + kThreads / 32 - 1) / (kThreads / 32));
+  k_argred_axis<T, IS_MAX><<<grid, kThreads, 0, st>>>(d, static_cast<const T *>(x), out, init);
+  return post_launch("k_argred_axis");
+}
+template <bool IS_MAX> static int argaxis_by_type(int dtype, const ArgAxisDesc &d, const void *x, int64_t *out, cudaStream_t st) {
+  switch (dtype) {
+    case NUK_F32: return argaxis_launch<float, IS_MAX>(d, x, out, st);
+    case NUK_F64: return argaxis_launch<double, IS_MAX>(d, x, out, st);
+    case NUK_I64: return argaxis_launch<int64_t, IS_MAX>(d, x, out, st);
+    case NUK_I32: return argaxis_launch<int32_t, IS_MAX>(d, x, out, st);
+    case NUK_I16: return argaxis_launch<int16_t, IS_MAX>(d, x, out, st);
+    case NUK_I8: return argaxis_launch<int8_t, IS_MAX>(d, x, out, st);
+    case NUK_U64: return argaxis_launch<uint64_t, IS_MAX>(d, x, out, st);
+    case NUK_U32: return argaxis_launch<uint32_t, IS_MAX>(d, x, out, st);
+    case NUK_U16: return argaxis_launch<uint16_t, IS_MAX>(d, x, out, st);
+    case NUK_U8: return argaxis_launch<uint8_t, IS_MAX>(d, x, out, st);
+  }
+  set_error(NUK_ERR_UNSUPPORTED, "arg-reduction: no kernel for dtype %d", dtype);
+  return NUK_ERR_UNSUPPORTED;
+}
+}  // namespace nuk
+
+NUK_API int nuk_argreduce(int is_max, int dtype, int rank, const int64_t *dims, const int64_t *sx, int axis,
+                          const int64_t *so, const void *x, int64_t *out, nuk_stream_t s) {
+  using namespace nuk;
+  if (rank < 1 || rank > NUK_MAX_RANK || axis < 0 || axis >= rank || !x || !out) {
+    set_error(NUK_ERR_INVALID, "bad arg-reduce descriptor (rank %d, axis %d)", rank, axis);
+    return NUK_ERR_INVALID;
+  }
+  if (!device_info()) return nuk_last_status();
+  ArgAxisDesc d;
+  memset(&d, 0, sizeof(d));
+  d.rlen = dims[axis];
+  d.rstride = sx[axis];
+  d.nout = 1;
+  int k = 0;
+  for (int a = 0; a < rank; ++a) {
+    if (a == axis) continue;
+    d.odims[k] = dims[a];
+    d.oxs[k] = sx[a];
+    d.oos[k] = so ? so[k] : 0;
+    d.nout *= dims[a];
+    ++k;
+  }
+  d.orank = k;
+  if (d.nout == 0) return NUK_OK;
+  return is_max ? argaxis_by_type<true>(dtype, d, x, out, (cudaStream_t)s)
+                : argaxis_by_type<false>(dtype, d, x, out, (cudaStream_t)s);
+}
