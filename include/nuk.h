@@ -166,6 +166,12 @@ int nuk_cmp2_scalar(int cmp, int dtype, int rank, const int64_t *dims, const int
 int nuk_fill(int dtype, int rank, const int64_t *dims, const int64_t *so,
              const void *host_scalar, void *out, nuk_stream_t s);
 
+/* fused left fold out = (((x0 op x1) op x2) ...) over nin (2..8) contiguous same-type arrays of n
+ * elements -- the n-ary nu:+ nu:- nu:* nu:/ nu:max nu:min in ONE pass instead of the reference's
+ * nin-1 passes over OUT (src/basic-math/n-arg-fn.lisp:59-88); same fold order and roundings, so
+ * bit-identical to the pass-by-pass fold.  out may alias any input. */
+int nuk_fold(int op, int dtype, int64_t n, int nin, const void *const *xs, void *out, nuk_stream_t s);
+
 /* ------------------------------------------------------------------ nd reductions
  * Reduce x over `axis` (or over everything when axis < 0) into out.
  * so[] are the element strides of OUT for the dims of x with `axis` removed (rank-1

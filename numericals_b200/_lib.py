@@ -93,6 +93,7 @@ def _declare(L):
         "nuk_reduce": [C.c_int, C.c_int, C.c_int, _i64p, _i64p, C.c_int, _i64p, _vp, _vp, C.c_int, _vp],
         "nuk_moments": [C.c_int, C.c_int, _i64p, _i64p, C.c_int, _i64p, _vp, _vp, _vp, C.c_int, _vp],
         "nuk_argreduce": [C.c_int, C.c_int, C.c_int, _i64p, _i64p, C.c_int, _i64p, _vp, _vp, _vp],
+        "nuk_fold": [C.c_int, C.c_int, C.c_int64, C.c_int, C.POINTER(_vp), _vp, _vp],
         "nuk_div_scalar_inplace": [C.c_int, C.c_int64, _vp, C.c_double, _vp],
         "nuk_variance_finish": [C.c_int, C.c_int64, _vp, _vp, C.c_double, C.c_double, _vp],
         "nuk_broadcast_resolve": [C.c_int, C.POINTER(C.c_int), C.POINTER(_i64p), C.POINTER(_i64p),

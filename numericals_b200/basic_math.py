@@ -416,6 +416,34 @@ def _nary_type(args, out):
     return et
 
 
+_FOLD_OPS = {}
+
+
+def _nary_fused(fn2, arrs, out, et):
+    """k >= 3 same-shape contiguous arrays: ONE pass (nuk_fold) instead of k-1 passes over OUT.
+    Same left-fold order and intermediate roundings, so identical results; returns None when the
+    operands do not qualify (broadcasting, scalars, views) and the caller folds pass by pass."""
+    if not _FOLD_OPS:
+        _FOLD_OPS.update({add: L.ADD, subtract: L.SUB, multiply: L.MUL, divide: L.DIV,
+                          two_arg_max: L.MAX, two_arg_min: L.MIN})
+    op = _FOLD_OPS.get(fn2)
+    if op is None or not config.fuse_nary or not 3 <= len(arrs) <= 8:
+        return None
+    if not all(isinstance(a, DenseArray) and a.is_contiguous() and a.element_type == et
+               and a.dimensions == arrs[0].dimensions and a.ptr % 16 == 0 for a in arrs):
+        return None
+    if op == L.DIV and not T.is_float(et):
+        return None
+    if out is None:
+        out = empty(arrs[0].dimensions, et)
+    elif not (out.is_contiguous() and out.dimensions == arrs[0].dimensions and out.element_type == et
+              and out.ptr % 16 == 0):
+        return None
+    ptrs = (C.c_void_p * len(arrs))(*[a.ptr for a in arrs])
+    L.check(L.lib().nuk_fold(op, T.code(et), out.total_size, len(arrs), ptrs, _vp(out.ptr), _stream()))
+    return out
+
+
 def _nary(fn2, identity_fn, args, out):
     """left fold of the binary op (src/basic-math/n-arg-fn.lisp:59-112)"""
     if not args:
@@ -429,6 +457,9 @@ def _nary(fn2, identity_fn, args, out):
     arrs = [a if _is_number(a) else asarray(a, type=et) for a in args]
     if len(arrs) == 1:
         return identity_fn(arrs[0], out)
+    fused = _nary_fused(fn2, arrs, out, et)
+    if fused is not None:
+        return fused
     acc = fn2(arrs[0], arrs[1], out=out, broadcast=True)
     for a in arrs[2:]:
         acc = fn2(acc, a, out=acc, broadcast=True)

@@ -24,6 +24,7 @@ class Config:
         self.multithreaded_threshold = 80000      # kept for API parity; the device has no use for it
         self.reduce_reference_order = False       # NUK_REDUCE_REF_ORDER for axis reductions
         self.fuse_variance = True                 # one-pass raw moments instead of 3 passes + temp
+        self.fuse_nary = True                     # nu:+ a b c ...: one pass (nuk_fold) instead of k-1
 
 
 config = Config()

@@ -65,3 +65,31 @@ def test_bitwise_family(nu):
         assert np.array_equal(nu.two_arg_logand(x[::2, ::-1], y[::2, :]).to_numpy(), a[::2, ::-1] & b[::2, :])
     with pytest.raises(nu.NoCFunction):
         nu.two_arg_logand(nu.zeros(3), nu.zeros(3))
+
+
+def test_fused_nary_fold_is_bit_identical_to_the_pass_by_pass_fold(nu):
+    """nu:+ a b c d :out o in one pass (nuk_fold) == the reference's k-1 passes, bit for bit"""
+    rng = np.random.default_rng(54)
+    for p in ("s", "d", "i32", "u8"):
+        dt = NP_OF[p]
+        hs = [rnd(rng, dt, (257, 1031)) for _ in range(5)]
+        xs = [nu.asarray(h, type=ETYPE_OF[p]) for h in hs]
+        for name in ("plus", "minus", "times", "max", "min") + (("slash",) if p in "sd" else ()):
+            f = getattr(nu, name)
+            nu.config.fuse_nary = True
+            fused = f(*xs).to_numpy()
+            out = nu.empty(xs[0].dimensions, ETYPE_OF[p])
+            assert f(*xs[:3], out=out) is out
+            nu.config.fuse_nary = False
+            try:
+                plain = f(*xs).to_numpy()
+                plain3 = f(*xs[:3]).to_numpy()
+            finally:
+                nu.config.fuse_nary = True
+            assert fused.tobytes() == plain.tobytes(), (p, name)
+            assert out.to_numpy().tobytes() == plain3.tobytes(), (p, name)
+    # in place: OUT aliases the first operand
+    a, b, c = (nu.asarray(rnd(rng, np.float32, 4099)) for _ in range(3))
+    want = (a.to_numpy() + b.to_numpy()) + c.to_numpy()
+    nu.plus(a, b, c, out=a)
+    assert a.to_numpy().tobytes() == want.tobytes()
