@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libnuk.so")
+LIB_PATH = os.environ.get("NUK_LIB") or os.path.join(_HERE, "lib", "libnuk.so")   # NUK_LIB: A/B builds in experiments
 
 NUK_MAX_RANK = 8
 NUK_OK = 0
