@@ -129,6 +129,10 @@ int nuk_host_register(void *hptr, size_t bytes); /* pin an existing buffer (e.g.
 int nuk_host_unregister(void *hptr);
 int nuk_pointer_is_device(const void *p);        /* 1 device/managed, 0 host */
 int nuk_flush_l2(nuk_stream_t s);                /* writes a > L2-sized scratch buffer (benchmark hygiene) */
+/* diagnostic: counts float bit patterns in [lo_bits, hi_bits) for which the MUFU-seeded reciprocal /
+   square root used inside the transcendental kernels differ from rcp.rn.f32 / sqrt.rn.f32 (expected 0
+   over the normal range 2^-100 .. 2^100); synchronous */
+int nuk_selftest_seeds(uint32_t lo_bits, uint32_t hi_bits, unsigned long long *mismatches, nuk_stream_t s);
 
 /* knobs (also readable from the environment at first use: NUK_GRID_MULT, NUK_STAGE_MB) */
 int nuk_set_option(const char *name, long value);

@@ -99,6 +99,7 @@ def _declare(L):
         "nuk_broadcast_resolve": [C.c_int, C.POINTER(C.c_int), C.POINTER(_i64p), C.POINTER(_i64p),
                                   C.POINTER(C.c_int), _i64p, _i64p],
         "nuk_coalesce": [C.c_int, C.c_int, _i64p, _i64p],
+        "nuk_selftest_seeds": [C.c_uint32, C.c_uint32, C.POINTER(C.c_ulonglong), _vp],
     }.items():
         fn = getattr(L, name)
         fn.argtypes = args

@@ -58,3 +58,37 @@ int launch_trans_f32(int op, int arity, const MapProblem &p) {
 }
 
 }  // namespace nuk
+
+// ---- self-test of the seed primitives: rcp_normal / sqrt_normal (MUFU seed + FMA step, no range
+// guard) against the IEEE instructions rcp.rn.f32 / sqrt.rn.f32 for every bit pattern in [lo, hi).
+// The host compile of the math headers uses 1.0f/d and sqrtf, so "device seed == IEEE" is what
+// makes the host ULP sweeps carry over to the device (tests/test_transcendental_gpu.py).
+namespace nuk {
+__global__ void k_selftest_seeds(uint32_t lo, uint64_t count, unsigned long long *mismatches) {
+  unsigned long long bad = 0;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x) {
+    const float x = __uint_as_float(lo + (uint32_t)i);
+    if (__float_as_uint(nukmath::rcp_normal(x)) != __float_as_uint(__frcp_rn(x))) ++bad;
+    if (__float_as_uint(nukmath::sqrt_normal(x)) != __float_as_uint(__fsqrt_rn(x))) ++bad;
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+}  // namespace nuk
+
+NUK_API int nuk_selftest_seeds(uint32_t lo_bits, uint32_t hi_bits, unsigned long long *mismatches, nuk_stream_t s) {
+  using namespace nuk;
+  if (!mismatches || hi_bits < lo_bits) {
+    set_error(NUK_ERR_INVALID, "nuk_selftest_seeds: bad arguments");
+    return NUK_ERR_INVALID;
+  }
+  if (!device_info()) return nuk_last_status();
+  void *d = nullptr;
+  NUK_TRY(scratch((cudaStream_t)s, sizeof(unsigned long long), &d));
+  NUK_CUDA(cudaMemsetAsync(d, 0, sizeof(unsigned long long), (cudaStream_t)s));
+  k_selftest_seeds<<<148 * 8, 256, 0, (cudaStream_t)s>>>(lo_bits, (uint64_t)hi_bits - lo_bits, (unsigned long long *)d);
+  NUK_CUDA(cudaGetLastError());
+  count_launch();
+  NUK_CUDA(cudaMemcpyAsync(mismatches, d, sizeof(unsigned long long), cudaMemcpyDeviceToHost, (cudaStream_t)s));
+  NUK_CUDA(cudaStreamSynchronize((cudaStream_t)s));
+  return NUK_OK;
+}

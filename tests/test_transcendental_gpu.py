@@ -96,6 +96,34 @@ def test_c2_functions_dense_bit_patterns(name, nu):
             assert got.tobytes() == host.tobytes(), (name, hex(b0), int((got != host).sum()))
 
 
+def test_seed_primitives_equal_ieee_on_every_normal_float(libnuk):
+    """rcp_normal / sqrt_normal (MUFU seed + FMA step, no range guard) == rcp.rn.f32 / sqrt.rn.f32 for
+    every float in [2^-100, 2^100) (1.68e9 bit patterns each): the host compile uses 1.0f/d and sqrtf,
+    so this is what lets the CPU sweeps speak for the seeded reciprocals / roots of nukmath_lite.cuh."""
+    bad = C.c_ulonglong(123)
+    st = libnuk.nuk_selftest_seeds(C.c_uint32(0x0D800000), C.c_uint32(0x71800000), C.byref(bad), libnuk.nuk_get_stream())
+    assert st == 0 and bad.value == 0, (st, bad.value)
+
+
+@pytest.mark.parametrize("name", ["tan", "asin", "acos", "atan", "sinh", "cosh", "asinh", "acosh", "atanh"])
+def test_lite_functions_dense_bit_patterns(name, nu):
+    """Every single-float in [2^-9, 4) (and negatives where defined), 2 x 75M bit patterns: device ==
+    host compile of nukmath_lite.cuh bit for bit (seeded reciprocal / root, magic-number rint)."""
+    lo, hi = 0x3B000000, 0x40800000
+    if name == "acosh":
+        lo, hi = 0x3F800000, 0x44800000       # [1, 1024)
+    step = 1 << 24
+    for sign in (0, 0x80000000):
+        if name == "acosh" and sign:
+            continue
+        for b0 in range(lo, hi, step):
+            x = (np.arange(b0, b0 + step, dtype=np.uint32) | np.uint32(sign)).view(np.float32)
+            got = device_unary(nu, name, x)
+            host = host_unary(name, x)
+            same = (got.view(np.uint32) == host.view(np.uint32)) | (np.isnan(got) & np.isnan(host))
+            assert same.all(), (name, hex(b0), int((~same).sum()))
+
+
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 def test_pow_atan2(dt, nu, oracle):
     from numericals_b200 import _lib
