@@ -43,6 +43,18 @@ template <class F> struct MapUnroll<F, std::void_t<decltype(F::kMapUnroll)>> {
   static constexpr int value = F::kMapUnroll;
 };
 
+// A functor that reads lookup tables declares kSmemBytes and stage(void *smem): every CTA copies the
+// tables into shared memory once (cooperatively) before its first element.
+template <class F, class = void> struct HasTables { static constexpr bool value = false; };
+template <class F> struct HasTables<F, std::void_t<decltype(F::kSmemBytes)>> { static constexpr bool value = true; };
+template <class F> NUK_D void stage_tables(F &f) {
+  if constexpr (HasTables<F>::value) {
+    __shared__ __align__(16) unsigned char smem[F::kSmemBytes];
+    f.stage(smem);
+    __syncthreads();
+  }
+}
+
 template <class F> NUK_D typename F::Out apply(const F &f, typename F::In a, typename F::In b) {
   if constexpr (F::kArity == 2) return f(a, b);
   else return f(a);
@@ -60,6 +72,7 @@ k_map_flat(size_t n, const typename F::In *x, const typename F::In *y, typename 
   using PIn = typename P::PIn;
   using POut = typename P::POut;
 
+  stage_tables(f);
   In xs = In(), ys = In();
   if (x_scalar) xs = x ? x[0] : scalar_as<In>(xv);
   if (F::kArity == 2 && y_scalar) ys = y ? y[0] : scalar_as<In>(yv);
@@ -177,6 +190,7 @@ k_map_rows(RowsDesc d, const typename F::In *x, const typename F::In *y, typenam
   using PIn = typename P::PIn;
   using POut = typename P::POut;
 
+  stage_tables(f);
   // blockIdx.y -> column tile; blockIdx.x -> (outer index, row group)
   const int64_t row_groups = (d.nrows + d.rows_per_cta - 1) / d.rows_per_cta;
   int64_t g = blockIdx.x;
@@ -265,6 +279,7 @@ __global__ void __launch_bounds__(kThreads)
 k_map_nd(size_t n, NdDesc d, const typename F::In *x, const typename F::In *y,
          typename F::Out *out, Scalar64 xv, Scalar64 yv, F f) {
   using In = typename F::In;
+  stage_tables(f);
   const size_t stride = (size_t)gridDim.x * kThreads;
   for (size_t i0 = (size_t)blockIdx.x * kThreads + threadIdx.x; i0 < n; i0 += stride * UNROLL) {
     In a[UNROLL], b[UNROLL];

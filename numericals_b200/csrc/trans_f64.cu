@@ -23,7 +23,23 @@ NUK_F64_UNARY(AsinD, asin_f64) NUK_F64_UNARY(AcosD, acos_f64) NUK_F64_UNARY(Atan
 NUK_F64_UNARY(SinhD, sinh_f64) NUK_F64_UNARY(CoshD, cosh_f64) NUK_F64_UNARY(TanhD, tanh_f64)
 NUK_F64_UNARY(AsinhD, asinh_f64) NUK_F64_UNARY(AcoshD, acosh_f64) NUK_F64_UNARY(AtanhD, atanh_f64)
 NUK_F64_UNARY(ExpD, exp_f64) NUK_F64_UNARY(LogD, log_f64)
-NUK_F64_BINARY(PowD, pow_f64) NUK_F64_BINARY(Atan2D, atan2_f64)
+NUK_F64_BINARY(Atan2D, atan2_f64)
+// table-driven functors: the 5 KB log/exp tables (nukmath_tab.cuh) are staged into shared memory per CTA
+struct TabStage {
+  static constexpr int kSmemBytes = nukmath::kTabBytes;
+  const uint64_t *tab;
+  NUK_D void stage(void *smem) {
+    uint64_t *s = static_cast<uint64_t *>(smem);
+    for (int w = threadIdx.x; w < NM_TAB_WORDS; w += blockDim.x) s[w] = nukmath::kTabImage[w];
+    tab = s;
+  }
+};
+struct PowD : TabStage {
+  using In = double; using Out = double;
+  static constexpr int kArity = 2;
+  static constexpr int kMapUnroll = 4;
+  NUK_D double operator()(double a, double b) const { return nukmath::pow_f64(a, b, tab); }
+};
 
 int launch_trans_f64(int op, int arity, const MapProblem &p) {
   if (arity == 2) {

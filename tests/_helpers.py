@@ -29,7 +29,7 @@ def build_host_tool(src, out, extra=()):
     os.makedirs(bdir, exist_ok=True)
     outp = os.path.join(bdir, out)
     srcp = os.path.join(HERE, "ulp", src)
-    hdrs = [os.path.join(ROOT, "numericals_b200", "csrc", h) for h in ("nukmath_f32.cuh", "nukmath_f64.cuh", "nukmath_lite.cuh")]
+    hdrs = [os.path.join(ROOT, "numericals_b200", "csrc", h) for h in ("nukmath_f32.cuh", "nukmath_f64.cuh", "nukmath_lite.cuh", "nukmath_tab.cuh", "nukmath_tables.inc")]
     deps = [srcp, os.path.join(HERE, "ulp", "ulp_sweep_f64.inc")] + hdrs
     if os.path.exists(outp) and all(os.path.getmtime(outp) >= os.path.getmtime(d) for d in deps):
         return outp
@@ -51,7 +51,7 @@ def hostmath():
         os.makedirs(bdir, exist_ok=True)
         outp = os.path.join(bdir, "libhostmath.so")
         srcp = os.path.join(HERE, "ulp", "hostmath.cpp")
-        hdrs = [os.path.join(ROOT, "numericals_b200", "csrc", h) for h in ("nukmath_f32.cuh", "nukmath_f64.cuh", "nukmath_lite.cuh")]
+        hdrs = [os.path.join(ROOT, "numericals_b200", "csrc", h) for h in ("nukmath_f32.cuh", "nukmath_f64.cuh", "nukmath_lite.cuh", "nukmath_tab.cuh", "nukmath_tables.inc")]
         if not os.path.exists(outp) or any(os.path.getmtime(outp) < os.path.getmtime(d) for d in [srcp] + hdrs):
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-mfma", "-ffp-contract=off", "-shared", "-fPIC",
                                    srcp, "-o", outp])
