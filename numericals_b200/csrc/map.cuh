@@ -72,7 +72,6 @@ k_map_flat(size_t n, const typename F::In *x, const typename F::In *y, typename 
   using PIn = typename P::PIn;
   using POut = typename P::POut;
 
-  stage_tables(f);
   In xs = In(), ys = In();
   if (x_scalar) xs = x ? x[0] : scalar_as<In>(xv);
   if (F::kArity == 2 && y_scalar) ys = y ? y[0] : scalar_as<In>(yv);
@@ -97,6 +96,7 @@ k_map_flat(size_t n, const typename F::In *x, const typename F::In *y, typename 
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) b[u] = ld_stream(yp + base + (size_t)u * kThreads);
     }
+    stage_tables(f);   // after the operand loads are in flight: the table copy hides under their latency
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
       POut r;
@@ -115,6 +115,7 @@ k_map_flat(size_t n, const typename F::In *x, const typename F::In *y, typename 
     }
   } else if (blockIdx.x < nfull) {
     // a scalar operand (uniform across the grid): same tile with broadcast values
+    stage_tables(f);
     const size_t base = (size_t)blockIdx.x * kTile + threadIdx.x;
     PIn a[UNROLL], b[UNROLL];
     if (!x_scalar) {
@@ -148,6 +149,7 @@ k_map_flat(size_t n, const typename F::In *x, const typename F::In *y, typename 
   }
   // remainder packs and the element tail: the last CTA
   if (blockIdx.x == nfull) {
+    stage_tables(f);
     for (size_t p = nfull * kTile + threadIdx.x; p < npack; p += kThreads) {
       PIn a, b;
       if (!x_scalar) a = ld_stream(xp + p);

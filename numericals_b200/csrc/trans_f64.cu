@@ -20,26 +20,40 @@ namespace nuk {
   };
 NUK_F64_UNARY(SinD, sin_f64) NUK_F64_UNARY(CosD, cos_f64) NUK_F64_UNARY(TanD, tan_f64)
 NUK_F64_UNARY(AsinD, asin_f64) NUK_F64_UNARY(AcosD, acos_f64) NUK_F64_UNARY(AtanD, atan_f64)
-NUK_F64_UNARY(SinhD, sinh_f64) NUK_F64_UNARY(CoshD, cosh_f64) NUK_F64_UNARY(TanhD, tanh_f64)
 NUK_F64_UNARY(AsinhD, asinh_f64) NUK_F64_UNARY(AcoshD, acosh_f64) NUK_F64_UNARY(AtanhD, atanh_f64)
-NUK_F64_UNARY(ExpD, exp_f64) NUK_F64_UNARY(LogD, log_f64)
 NUK_F64_BINARY(Atan2D, atan2_f64)
-// table-driven functors: the 5 KB log/exp tables (nukmath_tab.cuh) are staged into shared memory per CTA
-struct TabStage {
+// table-driven functors: the log/exp tables (nukmath_tab.cuh; words [W0, W1) of the 5 KB image) are
+// staged into shared memory once per CTA
+template <int W0, int W1> struct TabStage {
   static constexpr int kSmemBytes = nukmath::kTabBytes;
-  const uint64_t *tab;
+  nukmath::TabRef tab;
   NUK_D void stage(void *smem) {
     uint64_t *s = static_cast<uint64_t *>(smem);
-    for (int w = threadIdx.x; w < NM_TAB_WORDS; w += blockDim.x) s[w] = nukmath::kTabImage[w];
-    tab = s;
+    for (int w = W0 + threadIdx.x; w < W1; w += blockDim.x) s[w] = nukmath::kTabImage[w];
+    // opaque to the optimiser: otherwise the shared-window base (S2UR CgaCtaId + ULEA) is rebuilt per element
+    const uint32_t b = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("mov.u32 %0, %1;" : "=r"(tab.base) : "r"(b));
   }
 };
-struct PowD : TabStage {
+using TabAll = TabStage<0, NM_TAB_WORDS>;
+using TabLog = TabStage<0, 384>;
+using TabExp = TabStage<384, NM_TAB_WORDS>;
+struct PowD : TabAll {
   using In = double; using Out = double;
   static constexpr int kArity = 2;
   static constexpr int kMapUnroll = 4;
   NUK_D double operator()(double a, double b) const { return nukmath::pow_f64(a, b, tab); }
 };
+#define NUK_F64_TAB_UNARY(Name, FN, Stage)              \
+  struct Name : Stage {                                 \
+    using In = double; using Out = double;              \
+    static constexpr int kArity = 1;                    \
+    static constexpr int kMapUnroll = 4;                \
+    NUK_D double operator()(double a) const { return nukmath::FN(a, tab); } \
+  };
+NUK_F64_TAB_UNARY(ExpD, exp_f64, TabExp) NUK_F64_TAB_UNARY(LogD, log_f64, TabLog)
+NUK_F64_TAB_UNARY(SinhD, sinh_f64, TabExp) NUK_F64_TAB_UNARY(CoshD, cosh_f64, TabExp)
+NUK_F64_TAB_UNARY(TanhD, tanh_f64, TabExp)
 
 int launch_trans_f64(int op, int arity, const MapProblem &p) {
   if (arity == 2) {

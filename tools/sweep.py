@@ -31,7 +31,7 @@ def main():
     ap.add_argument("--log2n", type=int, default=28)
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--out", default=None)
-    ap.add_argument("--only", default=None, help="substring filter on the symbol name")
+    ap.add_argument("--only", default=None, help="comma-separated substrings of the symbol name (dexp,spow); ^d = prefix")
     args = ap.parse_args()
     nu.require_device(0)
     lib = _lib.lib()
@@ -94,7 +94,9 @@ def main():
     x, y, o = (P(b.ptr) for b in bufs)
 
     def want(sym):
-        return args.only is None or args.only in sym
+        if args.only is None:
+            return True
+        return any(sym.startswith(t[1:]) if t.startswith("^") else t in sym for t in args.only.split(","))
 
     for p in ALL:
         sz = SIZES[p]
