@@ -55,6 +55,12 @@ template <class F> NUK_D void stage_tables(F &f) {
   }
 }
 
+// minimum resident CTAs per SM the flat kernel is compiled for (caps registers): F::kMapMinBlocks
+template <class F, class = void> struct MapMinBlocks { static constexpr int value = 1; };
+template <class F> struct MapMinBlocks<F, std::void_t<decltype(F::kMapMinBlocks)>> {
+  static constexpr int value = F::kMapMinBlocks;
+};
+
 template <class F> NUK_D typename F::Out apply(const F &f, typename F::In a, typename F::In b) {
   if constexpr (F::kArity == 2) return f(a, b);
   else return f(a);
@@ -62,7 +68,7 @@ template <class F> NUK_D typename F::Out apply(const F &f, typename F::In a, typ
 
 // ------------------------------------------------------------------ flat kernel
 template <class F, int UNROLL>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, MapMinBlocks<F>::value)
 k_map_flat(size_t n, const typename F::In *x, const typename F::In *y, typename F::Out *out,
            int x_scalar, int y_scalar, Scalar64 xv, Scalar64 yv, F f) {
   using In = typename F::In;
