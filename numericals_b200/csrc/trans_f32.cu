@@ -4,6 +4,7 @@
 #include "dispatch.cuh"
 #include "nukmath_f32.cuh"
 #include "nukmath_f64.cuh"
+#include "tabstage.cuh"
 
 namespace nuk {
 
@@ -31,7 +32,16 @@ NUK_F32_UNARY_U(ExpF, exp_f32, 2)   // 5.9 TB/s with 2 packs per thread vs 5.2 w
 NUK_F32_VIA_F64(TanF, tan_f32) NUK_F32_VIA_F64(AsinF, asin_f32) NUK_F32_VIA_F64(AcosF, acos_f32)
 NUK_F32_VIA_F64(AtanF, atan_f32) NUK_F32_VIA_F64(SinhF, sinh_f32) NUK_F32_VIA_F64(CoshF, cosh_f32)
 NUK_F32_VIA_F64(AsinhF, asinh_f32) NUK_F32_VIA_F64(AcoshF, acosh_f32) NUK_F32_VIA_F64(AtanhF, atanh_f32)
-NUK_F32_BINARY(PowF, pow_f32) NUK_F32_BINARY(Atan2F, atan2_f32)
+NUK_F32_BINARY(Atan2F, atan2_f32)
+#ifndef NUK_POWF_UNROLL
+#define NUK_POWF_UNROLL 2
+#endif
+struct PowF : TabPowF {   // 640 bytes of tables in shared memory (nukmath_tab.cuh:pow_f32)
+  using In = float; using Out = float;
+  static constexpr int kArity = 2;
+  static constexpr int kMapUnroll = NUK_POWF_UNROLL;
+  NUK_D float operator()(float a, float b) const { return nukmath::pow_f32(a, b, tab); }
+};
 
 int launch_trans_f32(int op, int arity, const MapProblem &p) {
   if (arity == 2) {

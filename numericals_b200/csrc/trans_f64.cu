@@ -1,6 +1,7 @@
 // trans_f64.cu -- double-float transcendental maps, table src/transcendental/package.lisp:63-84.
 #include "dispatch.cuh"
 #include "nukmath_f64.cuh"
+#include "tabstage.cuh"
 
 namespace nuk {
 
@@ -22,29 +23,7 @@ NUK_F64_UNARY(SinD, sin_f64) NUK_F64_UNARY(CosD, cos_f64) NUK_F64_UNARY(TanD, ta
 NUK_F64_UNARY(AsinD, asin_f64) NUK_F64_UNARY(AcosD, acos_f64) NUK_F64_UNARY(AtanD, atan_f64)
 NUK_F64_UNARY(AsinhD, asinh_f64) NUK_F64_UNARY(AcoshD, acosh_f64) NUK_F64_UNARY(AtanhD, atanh_f64)
 NUK_F64_BINARY(Atan2D, atan2_f64)
-// table-driven functors: the log/exp tables (nukmath_tab.cuh; words [W0, W1) of the 5 KB image) are
-// staged into shared memory once per CTA
-template <int W0, int W1> struct TabStage {
-  static constexpr int kSmemBytes = nukmath::kTabBytes;
-  nukmath::TabRef tab;
-  NUK_D void stage(void *smem) {
-    // 16-byte copies, compile-time trip count (every map kernel runs kThreads threads per CTA)
-    static_assert(W0 % 2 == 0 && W1 % 2 == 0, "table ranges are 16-byte aligned");
-    const uint4 *g = reinterpret_cast<const uint4 *>(nukmath::kTabImage);
-    uint4 *s = static_cast<uint4 *>(smem);
-#pragma unroll
-    for (int w0 = W0 / 2; w0 < W1 / 2; w0 += kThreads) {
-      const int w = w0 + (int)threadIdx.x;
-      if (w < W1 / 2) s[w] = g[w];
-    }
-    // opaque to the optimiser: otherwise the shared-window base (S2UR CgaCtaId + ULEA) is rebuilt per element
-    const uint32_t b = (uint32_t)__cvta_generic_to_shared(smem);
-    asm volatile("mov.u32 %0, %1;" : "=r"(tab.base) : "r"(b));
-  }
-};
-using TabAll = TabStage<0, NM_TAB_WORDS>;
-using TabLog = TabStage<0, 384>;
-using TabExp = TabStage<384, NM_TAB_WORDS>;
+// table-driven functors (tabstage.cuh)
 #ifndef NUK_POW_UNROLL
 #define NUK_POW_UNROLL 4
 #endif

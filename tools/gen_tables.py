@@ -82,6 +82,40 @@ def exp_table():
     return rows
 
 
+# ---- single-float pow: 32-entry tables (logc and 2^(j/32) as doubles, 1/c as floats = 640 bytes)
+OFF32 = 0x3F360000          # z in [0.7109375, 1.421875); interval 18 = [1 - 2^-7, 1 + 2^-6) has c = 1
+
+
+def f2u32(f):
+    return struct.unpack("<I", struct.pack("<f", f))[0]
+
+
+def u2f32(u):
+    return struct.unpack("<f", struct.pack("<I", u))[0]
+
+
+def pow32_tables():
+    invc, logc, rmin, rmax = [], [], 0, 0
+    for i in range(32):
+        a = Fraction(u2f32(OFF32 + (i << 18)))
+        b = Fraction(u2f32(OFF32 + ((i + 1) << 18)))
+        if a < 1 < b:
+            c = Fraction(1)
+        else:
+            # 1/c rounded to 12 bits: z (24 bits) * invc is exact in double, so is z*invc - 1
+            c = Fraction(int(round(2 / (a + b) * 2 ** 12)), 2 ** 12)
+        assert float(c) == u2f32(f2u32(float(c)))
+        lo, hi = a * c - 1, b * c - 1
+        rmin, rmax = min(rmin, lo), max(rmax, hi)
+        invc.append(float(c))
+        logc.append(rd(-mp.log(mp.mpf(c.numerator) / c.denominator)))
+    expt = []
+    for j in range(32):
+        H = rd(mp.mpf(2) ** (mp.mpf(j) / 32))
+        expt.append((d2u(H) - (j << 47)) & 0xFFFFFFFFFFFFFFFF)
+    return invc, logc, expt, float(rmin), float(rmax)
+
+
 def hexd(x):
     return "0x%016xull" % d2u(float(x))
 
@@ -131,6 +165,29 @@ def main():
         assert len(words) == 640
         for k in range(0, 640, 4):
             f.write("  " + ", ".join(words[k:k + 4]) + (", \\\n" if k + 4 < 640 else " }\n"))
+    # ---- single-float pow
+    invc, logc, expt, r0, r1 = pow32_tables()
+    g32 = lambda t: (mp.log1p(t) - t) / t ** 2 if t != 0 else -mp.mpf(1) / 2
+    w32 = lambda t: t                                        # error relative to r
+    L32, el = remez.fit(g32, w32, r0 * 1.0001, r1 * 1.0001, 5, None, "f64", grid=600)
+    s32 = float(mp.log(2) / 64) * 1.002
+    E32, ee = remez.fit(ge, we, -s32, s32, 3, None, "f64", grid=600)
+    with open(out, "a") as f:
+        f.write("// ---- single-float pow: log1p(r) - r = r^2 L(r), r in [%.6g, %.6g], error relative to r 2^%.2f;\n" %
+                (r0, r1, float(mp.log(el, 2))))
+        f.write("// e^r - 1 - r = r^2 E(r), |r| <= %.6g, absolute error 2^%.2f\n" % (s32, float(mp.log(ee, 2))))
+        f.write("#define NM_TF_OFF 0x%08xu\n" % OFF32)
+        f.write("// kTabPF: L0..L4, E0..E2, ln2, 32/ln2, -ln2/32, 1.5*2^52\n")
+        consts = [float(c) for c in list(L32) + list(E32)] + [rd(mp.log(2)), rd(32 / mp.log(2)), rd(-mp.log(2) / 32), 1.5 * 2.0 ** 52]
+        f.write("#define NM_TABF_POLY { %s }\n" % ", ".join(c.hex() for c in consts))
+        f.write("// image (uint64 words): [0,32) log c; [32,64) bits(2^(j/32)) - (j << 47); [64,80) 1/c as 32 floats\n")
+        words = [hexd(v) for v in logc] + ["0x%016xull" % v for v in expt]
+        for k in range(0, 32, 2):
+            words.append("0x%016xull" % (f2u32(invc[k]) | (f2u32(invc[k + 1]) << 32)))
+        f.write("#define NM_TABF_WORDS 80\n#define NM_TABF_IMAGE { \\\n")
+        for k in range(0, 80, 4):
+            f.write("  " + ", ".join(words[k:k + 4]) + (", \\\n" if k + 4 < 80 else " }\n"))
+    print("pow32: r in [%g, %g], log poly 2^%.2f, exp poly 2^%.2f" % (r0, r1, float(mp.log(el, 2)), float(mp.log(ee, 2))))
     print("wrote", os.path.normpath(out))
     print("log: r in [%g, %g], poly err 2^%.2f; exp: poly err 2^%.2f" %
           (rmin, rmax, float(mp.log(eb, 2)), float(mp.log(ec, 2))))
