@@ -61,6 +61,19 @@ template <class F> struct MapMinBlocks<F, std::void_t<decltype(F::kMapMinBlocks)
   static constexpr int value = F::kMapMinBlocks;
 };
 
+// A functor may split itself into a BRANCH-FREE main path `fast(a [, b], bool &slow)` that is valid for
+// ordinary arguments and raises `slow` otherwise, and the complete operator() that handles everything.
+// The flat kernel then evaluates fast() for all the elements of a pack -- straight-line code, so the
+// compiler interleaves the independent dependency chains of the elements (the per-element special-case
+// branches of operator() pin instruction-level parallelism at 1 and leave the kernel latency-bound at
+// the 40-50 % occupancy these register-heavy functions get) -- and re-does flagged elements afterwards.
+template <class F, class = void> struct HasFast { static constexpr bool value = false; };
+template <class F> struct HasFast<F, std::void_t<decltype(F::kHasFast)>> { static constexpr bool value = F::kHasFast; };
+template <class F> NUK_D typename F::Out apply_fast(const F &f, typename F::In a, typename F::In b, bool &slow) {
+  if constexpr (F::kArity == 2) return f.fast(a, b, slow);
+  else return f.fast(a, slow);
+}
+
 template <class F> NUK_D typename F::Out apply(const F &f, typename F::In a, typename F::In b) {
   if constexpr (F::kArity == 2) return f(a, b);
   else return f(a);
@@ -113,6 +126,19 @@ k_map_flat(size_t n, const typename F::In *x, const typename F::In *y, typename 
 #pragma unroll
         for (int w = 0; w < 4; ++w) wr[w] = Word4<F>::op(wa[w], wb[w]);
         memcpy(&r, wr, 16);
+      } else if constexpr (HasFast<F>::value) {
+        bool slow[E], any = false;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          slow[e] = false;
+          r.v[e] = apply_fast(f, a[u].v[e], F::kArity == 2 ? b[u].v[e] : In(), slow[e]);
+          any |= slow[e];
+        }
+        if (any) {
+#pragma unroll
+          for (int e = 0; e < E; ++e)
+            if (slow[e]) r.v[e] = apply(f, a[u].v[e], F::kArity == 2 ? b[u].v[e] : In());
+        }
       } else {
 #pragma unroll
         for (int e = 0; e < E; ++e) r.v[e] = apply(f, a[u].v[e], F::kArity == 2 ? b[u].v[e] : In());

@@ -33,6 +33,9 @@ NUK_F32_VIA_F64(TanF, tan_f32) NUK_F32_VIA_F64(AsinF, asin_f32) NUK_F32_VIA_F64(
 NUK_F32_VIA_F64(AtanF, atan_f32) NUK_F32_VIA_F64(SinhF, sinh_f32) NUK_F32_VIA_F64(CoshF, cosh_f32)
 NUK_F32_VIA_F64(AsinhF, asinh_f32) NUK_F32_VIA_F64(AcoshF, acosh_f32) NUK_F32_VIA_F64(AtanhF, atanh_f32)
 NUK_F32_BINARY(Atan2F, atan2_f32)
+#ifndef NUK_POWF_MINB
+#define NUK_POWF_MINB 5    // 48 registers: 0.59 ms per 2^28 (83 %); uncapped (88 registers, 2 CTAs/SM) 0.89 ms
+#endif
 #ifndef NUK_POWF_UNROLL
 #define NUK_POWF_UNROLL 2
 #endif
@@ -40,7 +43,10 @@ struct PowF : TabPowF {   // 640 bytes of tables in shared memory (nukmath_tab.c
   using In = float; using Out = float;
   static constexpr int kArity = 2;
   static constexpr int kMapUnroll = NUK_POWF_UNROLL;
+  static constexpr int kMapMinBlocks = NUK_POWF_MINB;
+  static constexpr bool kHasFast = true;
   NUK_D float operator()(float a, float b) const { return nukmath::pow_f32(a, b, tab); }
+  NUK_D float fast(float a, float b, bool &slow) const { return nukmath::pow_f32_fast(a, b, tab, slow); }
 };
 
 int launch_trans_f32(int op, int arity, const MapProblem &p) {

@@ -24,21 +24,26 @@ NUK_F64_UNARY(AsinD, asin_f64) NUK_F64_UNARY(AcosD, acos_f64) NUK_F64_UNARY(Atan
 NUK_F64_UNARY(AsinhD, asinh_f64) NUK_F64_UNARY(AcoshD, acosh_f64) NUK_F64_UNARY(AtanhD, atanh_f64)
 NUK_F64_BINARY(Atan2D, atan2_f64)
 // table-driven functors (tabstage.cuh)
+#ifndef NUK_FAST_SPLIT
+#define NUK_FAST_SPLIT true
+#endif
 #ifndef NUK_POW_UNROLL
 #define NUK_POW_UNROLL 4
 #endif
 #ifndef NUK_POW_MINB
-#define NUK_POW_MINB 1
+#define NUK_POW_MINB 3     // 80 registers: 1.13 ms per 2^28 (87 %); 64 registers spill (1.46 ms), uncapped 90 regs 1.26 ms
 #endif
 #ifndef NUK_TANH_MINB
-#define NUK_TANH_MINB 5    // 48 registers instead of 82: 0.84 ms instead of 1.15 ms per 2^28 (profiles/)
+#define NUK_TANH_MINB 4    // 64 registers: 0.73 ms per 2^28 (90 %)
 #endif
 struct PowD : TabAll {
   using In = double; using Out = double;
   static constexpr int kArity = 2;
   static constexpr int kMapUnroll = NUK_POW_UNROLL;
   static constexpr int kMapMinBlocks = NUK_POW_MINB;
+  static constexpr bool kHasFast = NUK_FAST_SPLIT;
   NUK_D double operator()(double a, double b) const { return nukmath::pow_f64(a, b, tab); }
+  NUK_D double fast(double a, double b, bool &slow) const { return nukmath::pow_f64_fast(a, b, tab, slow); }
 };
 #define NUK_F64_TAB_UNARY(Name, FN, Stage)              \
   struct Name : Stage {                                 \
@@ -54,7 +59,9 @@ struct TanhD : TabExp {
   static constexpr int kArity = 1;
   static constexpr int kMapUnroll = 4;
   static constexpr int kMapMinBlocks = NUK_TANH_MINB;
+  static constexpr bool kHasFast = NUK_FAST_SPLIT;
   NUK_D double operator()(double a) const { return nukmath::tanh_f64(a, tab); }
+  NUK_D double fast(double a, bool &slow) const { return nukmath::tanh_f64_fast(a, tab, slow); }
 };
 
 int launch_trans_f64(int op, int arity, const MapProblem &p) {
