@@ -16,6 +16,29 @@ namespace nuk {
     NUK_D float operator()(float a) const { return nukmath::FN(a); } \
   };
 #define NUK_F32_UNARY(Name, FN) NUK_F32_UNARY_U(Name, FN, 4)
+// with a branch-free main path FN_fast (map.cuh:HasFast); MINB caps registers (resident CTAs per SM)
+#define NUK_F32_UNARY_FAST(Name, FN, UNR, MINB, ON)     \
+  struct Name {                                         \
+    using In = float; using Out = float;                \
+    static constexpr int kArity = 1;                    \
+    static constexpr int kMapUnroll = UNR;              \
+    static constexpr int kMapMinBlocks = (ON) ? MINB : 1; \
+    static constexpr bool kHasFast = ON;                \
+    NUK_D float operator()(float a) const { return nukmath::FN(a); } \
+    NUK_D float fast(float a, bool &slow) const { return nukmath::FN##_fast(a, slow); } \
+  };
+#ifndef NUK_F32_MINB
+#define NUK_F32_MINB 5
+#endif
+#ifndef NUK_FAST_TRIG32
+#define NUK_FAST_TRIG32 false   // measured slower with the split (profiles/fast_split_ab_r01.txt)
+#endif
+#ifndef NUK_FAST_HYP32
+#define NUK_FAST_HYP32 false   // measured slower with the split (profiles/fast_split_ab_r01.txt)
+#endif
+#ifndef NUK_FAST_ATAN2F
+#define NUK_FAST_ATAN2F false   // measured slower with the split (profiles/fast_split_ab_r01.txt)
+#endif
 // measured on B200 (profiles/time_unroll_r01.txt, 2^28 elements): 4 packs per thread beat 1 by 15-30 % for
 // every unary below (tan 5.2 vs 4.2 TB/s, cosh 5.2 vs 4.0), 2 packs are best for the binary ones
 #define NUK_F32_VIA_F64(Name, FN) NUK_F32_UNARY_U(Name, FN, 4)
@@ -26,13 +49,22 @@ namespace nuk {
     static constexpr int kMapUnroll = 2;                \
     NUK_D float operator()(float a, float b) const { return nukmath::FN(a, b); } \
   };
-NUK_F32_UNARY(SinF, sin_f32) NUK_F32_UNARY(CosF, cos_f32) NUK_F32_UNARY(TanhF, tanh_f32)
+NUK_F32_UNARY_FAST(SinF, sin_f32, 4, NUK_F32_MINB, NUK_FAST_TRIG32) NUK_F32_UNARY_FAST(CosF, cos_f32, 4, NUK_F32_MINB, NUK_FAST_TRIG32) NUK_F32_UNARY(TanhF, tanh_f32)
 NUK_F32_UNARY(LogF, log_f32)
 NUK_F32_UNARY_U(ExpF, exp_f32, 2)   // 5.9 TB/s with 2 packs per thread vs 5.2 with 4 (profiles/membench_r01.txt)
-NUK_F32_VIA_F64(TanF, tan_f32) NUK_F32_VIA_F64(AsinF, asin_f32) NUK_F32_VIA_F64(AcosF, acos_f32)
-NUK_F32_VIA_F64(AtanF, atan_f32) NUK_F32_VIA_F64(SinhF, sinh_f32) NUK_F32_VIA_F64(CoshF, cosh_f32)
-NUK_F32_VIA_F64(AsinhF, asinh_f32) NUK_F32_VIA_F64(AcoshF, acosh_f32) NUK_F32_VIA_F64(AtanhF, atanh_f32)
-NUK_F32_BINARY(Atan2F, atan2_f32)
+NUK_F32_UNARY_FAST(TanF, tan_f32, 4, NUK_F32_MINB, NUK_FAST_TRIG32) NUK_F32_VIA_F64(AsinF, asin_f32) NUK_F32_VIA_F64(AcosF, acos_f32)
+NUK_F32_VIA_F64(AtanF, atan_f32) NUK_F32_UNARY_FAST(SinhF, sinh_f32, 4, NUK_F32_MINB, NUK_FAST_HYP32) NUK_F32_UNARY_FAST(CoshF, cosh_f32, 4, NUK_F32_MINB, NUK_FAST_HYP32)
+NUK_F32_UNARY_FAST(AsinhF, asinh_f32, 4, NUK_F32_MINB, NUK_FAST_HYP32) NUK_F32_UNARY_FAST(AcoshF, acosh_f32, 4, NUK_F32_MINB, NUK_FAST_HYP32)
+NUK_F32_UNARY_FAST(AtanhF, atanh_f32, 4, NUK_F32_MINB, NUK_FAST_HYP32)
+struct Atan2F {
+  using In = float; using Out = float;
+  static constexpr int kArity = 2;
+  static constexpr int kMapUnroll = 2;
+  static constexpr int kMapMinBlocks = NUK_FAST_ATAN2F ? NUK_F32_MINB : 1;
+  static constexpr bool kHasFast = NUK_FAST_ATAN2F;
+  NUK_D float operator()(float a, float b) const { return nukmath::atan2_f32(a, b); }
+  NUK_D float fast(float a, float b, bool &slow) const { return nukmath::atan2_f32_fast(a, b, slow); }
+};
 #ifndef NUK_POWF_MINB
 #define NUK_POWF_MINB 5    // 48 registers: 0.59 ms per 2^28 (83 %); uncapped (88 registers, 2 CTAs/SM) 0.89 ms
 #endif

@@ -19,10 +19,45 @@ namespace nuk {
     static constexpr int kMapUnroll = 1;                \
     NUK_D double operator()(double a, double b) const { return nukmath::FN(a, b); } \
   };
-NUK_F64_UNARY(SinD, sin_f64) NUK_F64_UNARY(CosD, cos_f64) NUK_F64_UNARY(TanD, tan_f64)
-NUK_F64_UNARY(AsinD, asin_f64) NUK_F64_UNARY(AcosD, acos_f64) NUK_F64_UNARY(AtanD, atan_f64)
+#define NUK_F64_UNARY_FAST(Name, FN, MINB, ON)           \
+  struct Name {                                         \
+    using In = double; using Out = double;              \
+    static constexpr int kArity = 1;                    \
+    static constexpr int kMapUnroll = 2;                \
+    static constexpr int kMapMinBlocks = (ON) ? MINB : 1; \
+    static constexpr bool kHasFast = ON;                \
+    NUK_D double operator()(double a) const { return nukmath::FN(a); } \
+    NUK_D double fast(double a, bool &slow) const { return nukmath::FN##_fast(a, slow); } \
+  };
+#ifndef NUK_FAST_TRIG64
+#define NUK_FAST_TRIG64 true
+#endif
+#ifndef NUK_FAST_INV64
+#define NUK_FAST_INV64 true
+#endif
+#ifndef NUK_FAST_HYP64
+#define NUK_FAST_HYP64 true
+#endif
+// which functors take the split, and their register caps, were chosen by same-box A/B runs
+// (profiles/fast_split_ab_r01.txt): sin/tan +3, asin/acos/atan +4..7, atan2 +17, sinh/cosh +1 points of HBM peak;
+// cos and every single-float function except pow were faster without it
+#ifndef NUK_TRIG_MINB
+#define NUK_TRIG_MINB 4
+#endif
+NUK_F64_UNARY_FAST(SinD, sin_f64, 5, NUK_FAST_TRIG64) NUK_F64_UNARY_FAST(CosD, cos_f64, 5, false)
+NUK_F64_UNARY_FAST(TanD, tan_f64, 5, NUK_FAST_TRIG64)
+NUK_F64_UNARY_FAST(AsinD, asin_f64, NUK_TRIG_MINB, NUK_FAST_INV64) NUK_F64_UNARY_FAST(AcosD, acos_f64, NUK_TRIG_MINB, NUK_FAST_INV64)
+NUK_F64_UNARY_FAST(AtanD, atan_f64, NUK_TRIG_MINB, NUK_FAST_INV64)
 NUK_F64_UNARY(AsinhD, asinh_f64) NUK_F64_UNARY(AcoshD, acosh_f64) NUK_F64_UNARY(AtanhD, atanh_f64)
-NUK_F64_BINARY(Atan2D, atan2_f64)
+struct Atan2D {
+  using In = double; using Out = double;
+  static constexpr int kArity = 2;
+  static constexpr int kMapUnroll = 1;
+  static constexpr int kMapMinBlocks = NUK_FAST_INV64 ? 5 : 1;
+  static constexpr bool kHasFast = NUK_FAST_INV64;
+  NUK_D double operator()(double a, double b) const { return nukmath::atan2_f64(a, b); }
+  NUK_D double fast(double a, double b, bool &slow) const { return nukmath::atan2_f64_fast(a, b, slow); }
+};
 // table-driven functors (tabstage.cuh)
 #ifndef NUK_FAST_SPLIT
 #define NUK_FAST_SPLIT true
@@ -53,7 +88,17 @@ struct PowD : TabAll {
     NUK_D double operator()(double a) const { return nukmath::FN(a, tab); } \
   };
 NUK_F64_TAB_UNARY(ExpD, exp_f64, TabExp) NUK_F64_TAB_UNARY(LogD, log_f64, TabLog)
-NUK_F64_TAB_UNARY(SinhD, sinh_f64, TabExp) NUK_F64_TAB_UNARY(CoshD, cosh_f64, TabExp)
+#define NUK_F64_TAB_UNARY_FAST(Name, FN, Stage, MINB)    \
+  struct Name : Stage {                                 \
+    using In = double; using Out = double;              \
+    static constexpr int kArity = 1;                    \
+    static constexpr int kMapUnroll = 4;                \
+    static constexpr int kMapMinBlocks = NUK_FAST_HYP64 ? MINB : 1; \
+    static constexpr bool kHasFast = NUK_FAST_HYP64;    \
+    NUK_D double operator()(double a) const { return nukmath::FN(a, tab); } \
+    NUK_D double fast(double a, bool &slow) const { return nukmath::FN##_fast(a, tab, slow); } \
+  };
+NUK_F64_TAB_UNARY_FAST(SinhD, sinh_f64, TabExp, NUK_TANH_MINB) NUK_F64_TAB_UNARY_FAST(CoshD, cosh_f64, TabExp, NUK_TANH_MINB)
 struct TanhD : TabExp {
   using In = double; using Out = double;
   static constexpr int kArity = 1;
