@@ -56,7 +56,7 @@ template <class F> NUK_D void stage_tables(F &f) {
 }
 
 // minimum resident CTAs per SM the flat kernel is compiled for (caps registers): F::kMapMinBlocks
-template <class F, class = void> struct MapMinBlocks { static constexpr int value = 1; };
+template <class F, class = void> struct MapMinBlocks { static constexpr int value = 0; };   // 0 = unspecified (a 1 here made ptxas spend 55 registers on exp_f32 instead of 32)
 template <class F> struct MapMinBlocks<F, std::void_t<decltype(F::kMapMinBlocks)>> {
   static constexpr int value = F::kMapMinBlocks;
 };

@@ -22,7 +22,7 @@ namespace nuk {
     using In = float; using Out = float;                \
     static constexpr int kArity = 1;                    \
     static constexpr int kMapUnroll = UNR;              \
-    static constexpr int kMapMinBlocks = (ON) ? MINB : 1; \
+    static constexpr int kMapMinBlocks = (ON) ? MINB : 0; \
     static constexpr bool kHasFast = ON;                \
     NUK_D float operator()(float a) const { return nukmath::FN(a); } \
     NUK_D float fast(float a, bool &slow) const { return nukmath::FN##_fast(a, slow); } \
@@ -34,7 +34,7 @@ namespace nuk {
 #define NUK_FAST_TRIG32 false   // measured slower with the split (profiles/fast_split_ab_r01.txt)
 #endif
 #ifndef NUK_FAST_HYP32
-#define NUK_FAST_HYP32 false   // measured slower with the split (profiles/fast_split_ab_r01.txt)
+#define NUK_FAST_HYP32 true    // sinh cosh asinh acosh atanh: +2..3 points with the split and no register cap
 #endif
 #ifndef NUK_FAST_ATAN2F
 #define NUK_FAST_ATAN2F false   // measured slower with the split (profiles/fast_split_ab_r01.txt)
@@ -53,14 +53,14 @@ NUK_F32_UNARY_FAST(SinF, sin_f32, 4, NUK_F32_MINB, NUK_FAST_TRIG32) NUK_F32_UNAR
 NUK_F32_UNARY(LogF, log_f32)
 NUK_F32_UNARY_U(ExpF, exp_f32, 2)   // 5.9 TB/s with 2 packs per thread vs 5.2 with 4 (profiles/membench_r01.txt)
 NUK_F32_UNARY_FAST(TanF, tan_f32, 4, NUK_F32_MINB, NUK_FAST_TRIG32) NUK_F32_VIA_F64(AsinF, asin_f32) NUK_F32_VIA_F64(AcosF, acos_f32)
-NUK_F32_VIA_F64(AtanF, atan_f32) NUK_F32_UNARY_FAST(SinhF, sinh_f32, 4, NUK_F32_MINB, NUK_FAST_HYP32) NUK_F32_UNARY_FAST(CoshF, cosh_f32, 4, NUK_F32_MINB, NUK_FAST_HYP32)
-NUK_F32_UNARY_FAST(AsinhF, asinh_f32, 4, NUK_F32_MINB, NUK_FAST_HYP32) NUK_F32_UNARY_FAST(AcoshF, acosh_f32, 4, NUK_F32_MINB, NUK_FAST_HYP32)
-NUK_F32_UNARY_FAST(AtanhF, atanh_f32, 4, NUK_F32_MINB, NUK_FAST_HYP32)
+NUK_F32_VIA_F64(AtanF, atan_f32) NUK_F32_UNARY_FAST(SinhF, sinh_f32, 4, 0, NUK_FAST_HYP32) NUK_F32_UNARY_FAST(CoshF, cosh_f32, 4, 0, NUK_FAST_HYP32)
+NUK_F32_UNARY_FAST(AsinhF, asinh_f32, 4, 0, NUK_FAST_HYP32) NUK_F32_UNARY_FAST(AcoshF, acosh_f32, 4, 0, NUK_FAST_HYP32)
+NUK_F32_UNARY_FAST(AtanhF, atanh_f32, 4, 0, NUK_FAST_HYP32)
 struct Atan2F {
   using In = float; using Out = float;
   static constexpr int kArity = 2;
   static constexpr int kMapUnroll = 2;
-  static constexpr int kMapMinBlocks = NUK_FAST_ATAN2F ? NUK_F32_MINB : 1;
+  static constexpr int kMapMinBlocks = NUK_FAST_ATAN2F ? NUK_F32_MINB : 0;
   static constexpr bool kHasFast = NUK_FAST_ATAN2F;
   NUK_D float operator()(float a, float b) const { return nukmath::atan2_f32(a, b); }
   NUK_D float fast(float a, float b, bool &slow) const { return nukmath::atan2_f32_fast(a, b, slow); }

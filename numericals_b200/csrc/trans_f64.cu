@@ -24,7 +24,7 @@ namespace nuk {
     using In = double; using Out = double;              \
     static constexpr int kArity = 1;                    \
     static constexpr int kMapUnroll = 2;                \
-    static constexpr int kMapMinBlocks = (ON) ? MINB : 1; \
+    static constexpr int kMapMinBlocks = (ON) ? MINB : 0; \
     static constexpr bool kHasFast = ON;                \
     NUK_D double operator()(double a) const { return nukmath::FN(a); } \
     NUK_D double fast(double a, bool &slow) const { return nukmath::FN##_fast(a, slow); } \
@@ -39,21 +39,21 @@ namespace nuk {
 #define NUK_FAST_HYP64 true
 #endif
 // which functors take the split, and their register caps, were chosen by same-box A/B runs
-// (profiles/fast_split_ab_r01.txt): sin/tan +3, asin/acos/atan +4..7, atan2 +17, sinh/cosh +1 points of HBM peak;
-// cos and every single-float function except pow were faster without it
+// (profiles/fast_split_ab_r01.txt): atan2 +16, atan +5, asin/acos/tan/cosh +1 points of HBM peak; sin, cos, sinh
+// and the single-float trig/atan2 kernels were faster without it
 #ifndef NUK_TRIG_MINB
 #define NUK_TRIG_MINB 4
 #endif
-NUK_F64_UNARY_FAST(SinD, sin_f64, 5, NUK_FAST_TRIG64) NUK_F64_UNARY_FAST(CosD, cos_f64, 5, false)
+NUK_F64_UNARY_FAST(SinD, sin_f64, 5, false) NUK_F64_UNARY_FAST(CosD, cos_f64, 5, false)
 NUK_F64_UNARY_FAST(TanD, tan_f64, 5, NUK_FAST_TRIG64)
-NUK_F64_UNARY_FAST(AsinD, asin_f64, NUK_TRIG_MINB, NUK_FAST_INV64) NUK_F64_UNARY_FAST(AcosD, acos_f64, NUK_TRIG_MINB, NUK_FAST_INV64)
+NUK_F64_UNARY_FAST(AsinD, asin_f64, 0, NUK_FAST_INV64) NUK_F64_UNARY_FAST(AcosD, acos_f64, 0, NUK_FAST_INV64)
 NUK_F64_UNARY_FAST(AtanD, atan_f64, NUK_TRIG_MINB, NUK_FAST_INV64)
 NUK_F64_UNARY(AsinhD, asinh_f64) NUK_F64_UNARY(AcoshD, acosh_f64) NUK_F64_UNARY(AtanhD, atanh_f64)
 struct Atan2D {
   using In = double; using Out = double;
   static constexpr int kArity = 2;
   static constexpr int kMapUnroll = 1;
-  static constexpr int kMapMinBlocks = NUK_FAST_INV64 ? 5 : 1;
+  static constexpr int kMapMinBlocks = 0;
   static constexpr bool kHasFast = NUK_FAST_INV64;
   NUK_D double operator()(double a, double b) const { return nukmath::atan2_f64(a, b); }
   NUK_D double fast(double a, double b, bool &slow) const { return nukmath::atan2_f64_fast(a, b, slow); }
@@ -93,12 +93,12 @@ NUK_F64_TAB_UNARY(ExpD, exp_f64, TabExp) NUK_F64_TAB_UNARY(LogD, log_f64, TabLog
     using In = double; using Out = double;              \
     static constexpr int kArity = 1;                    \
     static constexpr int kMapUnroll = 4;                \
-    static constexpr int kMapMinBlocks = NUK_FAST_HYP64 ? MINB : 1; \
+    static constexpr int kMapMinBlocks = NUK_FAST_HYP64 ? MINB : 0; \
     static constexpr bool kHasFast = NUK_FAST_HYP64;    \
     NUK_D double operator()(double a) const { return nukmath::FN(a, tab); } \
     NUK_D double fast(double a, bool &slow) const { return nukmath::FN##_fast(a, tab, slow); } \
   };
-NUK_F64_TAB_UNARY_FAST(SinhD, sinh_f64, TabExp, NUK_TANH_MINB) NUK_F64_TAB_UNARY_FAST(CoshD, cosh_f64, TabExp, NUK_TANH_MINB)
+NUK_F64_TAB_UNARY(SinhD, sinh_f64, TabExp) NUK_F64_TAB_UNARY_FAST(CoshD, cosh_f64, TabExp, NUK_TANH_MINB)
 struct TanhD : TabExp {
   using In = double; using Out = double;
   static constexpr int kArity = 1;
