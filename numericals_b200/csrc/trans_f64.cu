@@ -48,7 +48,6 @@ NUK_F64_UNARY_FAST(SinD, sin_f64, 5, false) NUK_F64_UNARY_FAST(CosD, cos_f64, 5,
 NUK_F64_UNARY_FAST(TanD, tan_f64, 5, NUK_FAST_TRIG64)
 NUK_F64_UNARY_FAST(AsinD, asin_f64, 0, NUK_FAST_INV64) NUK_F64_UNARY_FAST(AcosD, acos_f64, 0, NUK_FAST_INV64)
 NUK_F64_UNARY_FAST(AtanD, atan_f64, NUK_TRIG_MINB, NUK_FAST_INV64)
-NUK_F64_UNARY(AsinhD, asinh_f64) NUK_F64_UNARY(AcoshD, acosh_f64) NUK_F64_UNARY(AtanhD, atanh_f64)
 struct Atan2D {
   using In = double; using Out = double;
   static constexpr int kArity = 2;
@@ -98,6 +97,25 @@ NUK_F64_TAB_UNARY(ExpD, exp_f64, TabExp) NUK_F64_TAB_UNARY(LogD, log_f64, TabLog
     NUK_D double operator()(double a) const { return nukmath::FN(a, tab); } \
     NUK_D double fast(double a, bool &slow) const { return nukmath::FN##_fast(a, tab, slow); } \
   };
+#ifndef NUK_FAST_IHYP64
+#define NUK_FAST_IHYP64 true
+#endif
+#ifndef NUK_IHYP_MINB
+#define NUK_IHYP_MINB 4
+#endif
+#define NUK_F64_TAB_UNARY_FAST2(Name, FN, Stage, MINB, ON) \
+  struct Name : Stage {                                 \
+    using In = double; using Out = double;              \
+    static constexpr int kArity = 1;                    \
+    static constexpr int kMapUnroll = 4;                \
+    static constexpr int kMapMinBlocks = (ON) ? MINB : 0; \
+    static constexpr bool kHasFast = ON;                \
+    NUK_D double operator()(double a) const { return nukmath::FN(a, tab); } \
+    NUK_D double fast(double a, bool &slow) const { return nukmath::FN##_fast(a, tab, slow); } \
+  };
+NUK_F64_TAB_UNARY_FAST2(AsinhD, asinh_f64, TabLog, NUK_IHYP_MINB, NUK_FAST_IHYP64)
+NUK_F64_TAB_UNARY_FAST2(AcoshD, acosh_f64, TabLog, NUK_IHYP_MINB, NUK_FAST_IHYP64)
+NUK_F64_TAB_UNARY_FAST2(AtanhD, atanh_f64, TabLog, NUK_IHYP_MINB, NUK_FAST_IHYP64)
 NUK_F64_TAB_UNARY(SinhD, sinh_f64, TabExp) NUK_F64_TAB_UNARY_FAST(CoshD, cosh_f64, TabExp, NUK_TANH_MINB)
 struct TanhD : TabExp {
   using In = double; using Out = double;
