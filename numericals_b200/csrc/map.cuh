@@ -57,9 +57,13 @@ template <class F> NUK_D void stage_tables(F &f) {
 
 // minimum resident CTAs per SM the flat kernel is compiled for (caps registers): F::kMapMinBlocks
 template <class F, class = void> struct MapMinBlocks { static constexpr int value = 0; };   // 0 = unspecified (a 1 here made ptxas spend 55 registers on exp_f32 instead of 32)
+#if defined(NUK_MINB_OVERRIDE)   // register-cap experiments: one value for every functor of the translation unit
+template <class F> struct MapMinBlocks<F, std::void_t<decltype(F::kArity)>> { static constexpr int value = NUK_MINB_OVERRIDE; };
+#else
 template <class F> struct MapMinBlocks<F, std::void_t<decltype(F::kMapMinBlocks)>> {
   static constexpr int value = F::kMapMinBlocks;
 };
+#endif
 
 // A functor may split itself into a BRANCH-FREE main path `fast(a [, b], bool &slow)` that is valid for
 // ordinary arguments and raises `slow` otherwise, and the complete operator() that handles everything.

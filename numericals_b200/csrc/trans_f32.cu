@@ -22,7 +22,7 @@ namespace nuk {
     using In = float; using Out = float;                \
     static constexpr int kArity = 1;                    \
     static constexpr int kMapUnroll = UNR;              \
-    static constexpr int kMapMinBlocks = (ON) ? MINB : 0; \
+    static constexpr int kMapMinBlocks = MINB;          \
     static constexpr bool kHasFast = ON;                \
     NUK_D float operator()(float a) const { return nukmath::FN(a); } \
     NUK_D float fast(float a, bool &slow) const { return nukmath::FN##_fast(a, slow); } \
@@ -49,10 +49,11 @@ namespace nuk {
     static constexpr int kMapUnroll = 2;                \
     NUK_D float operator()(float a, float b) const { return nukmath::FN(a, b); } \
   };
-NUK_F32_UNARY_FAST(SinF, sin_f32, 4, NUK_F32_MINB, NUK_FAST_TRIG32) NUK_F32_UNARY_FAST(CosF, cos_f32, 4, NUK_F32_MINB, NUK_FAST_TRIG32) NUK_F32_UNARY(TanhF, tanh_f32)
+// sin / cos capped at 32 registers (cos 92 -> 97 %, profiles/minblocks_sweep_r01.txt)
+NUK_F32_UNARY_FAST(SinF, sin_f32, 4, 8, NUK_FAST_TRIG32) NUK_F32_UNARY_FAST(CosF, cos_f32, 4, 8, NUK_FAST_TRIG32) NUK_F32_UNARY(TanhF, tanh_f32)
 NUK_F32_UNARY(LogF, log_f32)
 NUK_F32_UNARY_U(ExpF, exp_f32, 2)   // 5.9 TB/s with 2 packs per thread vs 5.2 with 4 (profiles/membench_r01.txt)
-NUK_F32_UNARY_FAST(TanF, tan_f32, 4, NUK_F32_MINB, NUK_FAST_TRIG32) NUK_F32_VIA_F64(AsinF, asin_f32) NUK_F32_VIA_F64(AcosF, acos_f32)
+NUK_F32_UNARY_FAST(TanF, tan_f32, 4, 0, NUK_FAST_TRIG32) NUK_F32_VIA_F64(AsinF, asin_f32) NUK_F32_VIA_F64(AcosF, acos_f32)
 NUK_F32_VIA_F64(AtanF, atan_f32) NUK_F32_UNARY_FAST(SinhF, sinh_f32, 4, 0, NUK_FAST_HYP32) NUK_F32_UNARY_FAST(CoshF, cosh_f32, 4, 0, NUK_FAST_HYP32)
 NUK_F32_UNARY_FAST(AsinhF, asinh_f32, 4, 0, NUK_FAST_HYP32) NUK_F32_UNARY_FAST(AcoshF, acosh_f32, 4, 0, NUK_FAST_HYP32)
 NUK_F32_UNARY_FAST(AtanhF, atanh_f32, 4, 0, NUK_FAST_HYP32)

@@ -24,7 +24,7 @@ namespace nuk {
     using In = double; using Out = double;              \
     static constexpr int kArity = 1;                    \
     static constexpr int kMapUnroll = 2;                \
-    static constexpr int kMapMinBlocks = (ON) ? MINB : 0; \
+    static constexpr int kMapMinBlocks = MINB;          \
     static constexpr bool kHasFast = ON;                \
     NUK_D double operator()(double a) const { return nukmath::FN(a); } \
     NUK_D double fast(double a, bool &slow) const { return nukmath::FN##_fast(a, slow); } \
@@ -44,7 +44,8 @@ namespace nuk {
 #ifndef NUK_TRIG_MINB
 #define NUK_TRIG_MINB 4
 #endif
-NUK_F64_UNARY_FAST(SinD, sin_f64, 5, false) NUK_F64_UNARY_FAST(CosD, cos_f64, 5, false)
+// cos capped at 32 registers: 74 -> 86 % (profiles/minblocks_sweep_r01.txt)
+NUK_F64_UNARY_FAST(SinD, sin_f64, 0, false) NUK_F64_UNARY_FAST(CosD, cos_f64, 8, false)
 NUK_F64_UNARY_FAST(TanD, tan_f64, 5, NUK_FAST_TRIG64)
 NUK_F64_UNARY_FAST(AsinD, asin_f64, 0, NUK_FAST_INV64) NUK_F64_UNARY_FAST(AcosD, acos_f64, 0, NUK_FAST_INV64)
 NUK_F64_UNARY_FAST(AtanD, atan_f64, NUK_TRIG_MINB, NUK_FAST_INV64)
@@ -52,7 +53,7 @@ struct Atan2D {
   using In = double; using Out = double;
   static constexpr int kArity = 2;
   static constexpr int kMapUnroll = 1;
-  static constexpr int kMapMinBlocks = 0;
+  static constexpr int kMapMinBlocks = 5;
   static constexpr bool kHasFast = NUK_FAST_INV64;
   NUK_D double operator()(double a, double b) const { return nukmath::atan2_f64(a, b); }
   NUK_D double fast(double a, double b, bool &slow) const { return nukmath::atan2_f64_fast(a, b, slow); }
@@ -79,14 +80,15 @@ struct PowD : TabAll {
   NUK_D double operator()(double a, double b) const { return nukmath::pow_f64(a, b, tab); }
   NUK_D double fast(double a, double b, bool &slow) const { return nukmath::pow_f64_fast(a, b, tab, slow); }
 };
-#define NUK_F64_TAB_UNARY(Name, FN, Stage)              \
+#define NUK_F64_TAB_UNARY(Name, FN, Stage, MINB)        \
   struct Name : Stage {                                 \
     using In = double; using Out = double;              \
     static constexpr int kArity = 1;                    \
     static constexpr int kMapUnroll = 4;                \
+    static constexpr int kMapMinBlocks = MINB;          \
     NUK_D double operator()(double a) const { return nukmath::FN(a, tab); } \
   };
-NUK_F64_TAB_UNARY(ExpD, exp_f64, TabExp) NUK_F64_TAB_UNARY(LogD, log_f64, TabLog)
+NUK_F64_TAB_UNARY(ExpD, exp_f64, TabExp, 6) NUK_F64_TAB_UNARY(LogD, log_f64, TabLog, 8)
 #define NUK_F64_TAB_UNARY_FAST(Name, FN, Stage, MINB)    \
   struct Name : Stage {                                 \
     using In = double; using Out = double;              \
@@ -116,7 +118,7 @@ NUK_F64_TAB_UNARY(ExpD, exp_f64, TabExp) NUK_F64_TAB_UNARY(LogD, log_f64, TabLog
 NUK_F64_TAB_UNARY_FAST2(AsinhD, asinh_f64, TabLog, NUK_IHYP_MINB, NUK_FAST_IHYP64)
 NUK_F64_TAB_UNARY_FAST2(AcoshD, acosh_f64, TabLog, NUK_IHYP_MINB, NUK_FAST_IHYP64)
 NUK_F64_TAB_UNARY_FAST2(AtanhD, atanh_f64, TabLog, NUK_IHYP_MINB, NUK_FAST_IHYP64)
-NUK_F64_TAB_UNARY(SinhD, sinh_f64, TabExp) NUK_F64_TAB_UNARY_FAST(CoshD, cosh_f64, TabExp, NUK_TANH_MINB)
+NUK_F64_TAB_UNARY(SinhD, sinh_f64, TabExp, 6) NUK_F64_TAB_UNARY_FAST(CoshD, cosh_f64, TabExp, 5)
 struct TanhD : TabExp {
   using In = double; using Out = double;
   static constexpr int kArity = 1;
