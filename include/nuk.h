@@ -68,6 +68,9 @@ enum { /* two-arg, same-type result: two-arg-fn/non-comparison, two-arg-fn/float
   NUK_ADD = 0, NUK_SUB, NUK_MUL, NUK_DIV, NUK_MAX, NUK_MIN,
   NUK_POW, NUK_ATAN2,
   NUK_AND, NUK_OR, NUK_XOR, NUK_ANDNOT, NUK_SRA,
+  /* log(x) / log(y) in ONE pass, bit-identical to the reference's three (nu:log x y = log y, log x, divide:
+   * src/transcendental/two-arg-fn-float.lisp:531-547) -- SURVEY 8f-1; float dtypes only */
+  NUK_LOGB,
   NUK_OP2_COUNT
 };
 enum { /* two-arg-fn/comparison -> (unsigned-byte 8) 0/1 */

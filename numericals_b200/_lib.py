@@ -18,7 +18,7 @@ NUK_OK = 0
 F32, F64, I64, I32, I16, I8, U64, U32, U16, U8 = 0, 1, 3, 4, 5, 6, 7, 8, 9, 10
 
 # ops (include/nuk.h)
-(ADD, SUB, MUL, DIV, MAX, MIN, POW, ATAN2, AND, OR, XOR, ANDNOT, SRA) = range(13)
+(ADD, SUB, MUL, DIV, MAX, MIN, POW, ATAN2, AND, OR, XOR, ANDNOT, SRA, LOGB) = range(14)
 (LT, LE, EQ, NEQ, GE, GT) = range(6)
 (COPY, ABS, ROUND, TRUNC, FLOOR, CEIL, SQRT, SIN, COS, TAN, ASIN, ACOS, ATAN, SINH, COSH, TANH,
  ASINH, ACOSH, ATANH, EXP, LOG, NOT) = range(22)

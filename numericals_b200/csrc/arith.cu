@@ -88,7 +88,7 @@ int launch_op2(int op, int dtype, const MapProblem &p) {
   switch (op) {
     case NUK_ADD: case NUK_SUB: case NUK_MUL: case NUK_DIV: case NUK_MAX: case NUK_MIN:
       return launch_arith(op, dtype, p);
-    case NUK_POW: case NUK_ATAN2:
+    case NUK_POW: case NUK_ATAN2: case NUK_LOGB:
       if (dtype == NUK_F32) return launch_trans_f32(op, 2, p);
       if (dtype == NUK_F64) return launch_trans_f64(op, 2, p);
       set_error(NUK_ERR_UNSUPPORTED, "op %d needs a float dtype, got %d", op, dtype);

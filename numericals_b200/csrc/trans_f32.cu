@@ -82,8 +82,18 @@ struct PowF : TabPowF {   // 640 bytes of tables in shared memory (nukmath_tab.c
   NUK_D float fast(float a, float b, bool &slow) const { return nukmath::pow_f32_fast(a, b, tab, slow); }
 };
 
+// nu:log x y = log(x) / log(y) in one pass; IEEE division of the two rounded logs, so the bits are those of
+// the reference's log, log, divide sequence (src/transcendental/two-arg-fn-float.lisp:531-547)
+struct LogbF {
+  using In = float; using Out = float;
+  static constexpr int kArity = 2;
+  static constexpr int kMapUnroll = 2;
+  NUK_D float operator()(float a, float b) const { return nukmath::log_f32(a) / nukmath::log_f32(b); }
+};
+
 int launch_trans_f32(int op, int arity, const MapProblem &p) {
   if (arity == 2) {
+    if (op == NUK_LOGB) return launch_map<LogbF>(p);
     if (op == NUK_POW) return launch_map<PowF>(p);
     if (op == NUK_ATAN2) return launch_map<Atan2F>(p);
   } else {

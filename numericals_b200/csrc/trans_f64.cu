@@ -129,8 +129,17 @@ struct TanhD : TabExp {
   NUK_D double fast(double a, bool &slow) const { return nukmath::tanh_f64_fast(a, tab, slow); }
 };
 
+// nu:log x y in one pass (see LogbF); both logs from the shared-memory table
+struct LogbD : TabLog {
+  using In = double; using Out = double;
+  static constexpr int kArity = 2;
+  static constexpr int kMapUnroll = 2;
+  NUK_D double operator()(double a, double b) const { return nukmath::log_f64(a, tab) / nukmath::log_f64(b, tab); }
+};
+
 int launch_trans_f64(int op, int arity, const MapProblem &p) {
   if (arity == 2) {
+    if (op == NUK_LOGB) return launch_map<LogbD>(p);
     if (op == NUK_POW) return launch_map<PowD>(p);
     if (op == NUK_ATAN2) return launch_map<Atan2D>(p);
   } else {

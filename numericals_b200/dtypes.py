@@ -119,6 +119,7 @@ class NoCFunction(LookupError):
 TWO_ARG = {"add": (L.ADD, "add"), "subtract": (L.SUB, "sub"), "multiply": (L.MUL, "mul"),
            "divide": (L.DIV, "div"), "two-arg-max": (L.MAX, "max"), "two-arg-min": (L.MIN, "min"),
            "expt": (L.POW, "pow"), "atan2": (L.ATAN2, "atan2"),
+           "log-base": (L.LOGB, "log"),      # fused nu:log x y (nuk_map2 only; the BMAS table has no such row)
            "two-arg-logand": (L.AND, "and"), "two-arg-logior": (L.OR, "or"),
            "two-arg-logxor": (L.XOR, "xor"), "logandc1": (L.ANDNOT, "andnot")}
 COMPARE = {"two-arg-<": (L.LT, "lt"), "two-arg-<=": (L.LE, "le"), "two-arg-=": (L.EQ, "eq"),
@@ -131,7 +132,7 @@ ONE_ARG = {"abs": (L.ABS, "abs"), "fround": (L.ROUND, "round"), "ftruncate": (L.
            "asinh": (L.ASINH, "asinh"), "acosh": (L.ACOSH, "acosh"), "atanh": (L.ATANH, "atanh"),
            "exp": (L.EXP, "exp"), "log": (L.LOG, "log"), "lognot": (L.NOT, "not"), "copy": (L.COPY, "copy")}
 REDUCE = {"sum": (L.SUM, "sum"), "maximum": (L.HMAX, "hmax"), "minimum": (L.HMIN, "hmin")}
-_FLOAT_ONLY = {"divide", "expt", "atan2", "fround", "ftruncate", "ffloor", "fceiling", "sqrt", "sin", "cos",
+_FLOAT_ONLY = {"divide", "expt", "atan2", "log-base", "fround", "ftruncate", "ffloor", "fceiling", "sqrt", "sin", "cos",
                "tan", "asin", "acos", "atan", "sinh", "cosh", "tanh", "asinh", "acosh", "atanh", "exp", "log"}
 _INT_ONLY = {"two-arg-logand", "two-arg-logior", "two-arg-logxor", "logandc1", "lognot"}
 _SIGNED_SYMBOL = {"add", "subtract", "abs", "sum", "copy"}  # unsigned arrays use the i* symbol

@@ -62,13 +62,16 @@ def atan(x, y=None, out=None, broadcast=None):
 
 
 def log(x, base=None, out=None, broadcast=None):
-    """nu:log: natural log, or log(x)/log(base) composed from two maps and a divide
-    (two-arg-fn-float.lisp:531-547)"""
+    """nu:log: natural log, or log(x)/log(base).  The reference composes the latter from two maps and a
+    divide (two-arg-fn-float.lisp:531-547: 28 bytes per single-float element); for two arrays it is ONE map
+    here (NUK_LOGB: 12 bytes per element, the same bits -- an IEEE division of the two rounded logs)."""
     if base is None:
         return _log1(x, out=out, broadcast=broadcast)
-    lx = _log1(x, out=out, broadcast=broadcast)
-    lb = _log1(base) if not _is_number(base) else __import__("math").log(base)
-    return divide(lx, lb, out=lx, broadcast=True)
+    if _is_number(base) or _is_number(x):
+        lx = _log1(x, out=out, broadcast=broadcast)
+        lb = _log1(base) if not _is_number(base) else __import__("math").log(base)
+        return divide(lx, lb, out=lx, broadcast=True)
+    return _two_arg_float("log-base", x, base, out, broadcast)
 
 
 # in-place operators (src/transcendental/in-place-operators.lisp:3-27); unary in-place forces :broadcast nil

@@ -137,3 +137,29 @@ def test_rows_and_nd_kernels_stage_the_tables(name, dt, nu):
         rev = nu.asarray(a[:, ::-1].copy(), type=dt)
         got = fn(rev.aref(slice(None), slice(None, None, -1))).to_numpy()   # negative inner stride: nd kernel
         assert same_bits(got, flat).all()
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_two_arg_log_is_one_pass_with_the_bits_of_three(dt, nu):
+    """nu:log x y (two-arg-fn-float.lisp:531-547: log y, log x, divide) as ONE map == the three-pass bits"""
+    rng = np.random.default_rng(11)
+    r, c = 257, 1031
+    x = np.concatenate([(rng.random(r * c - 8) * 100 + 1e-3), [0.0, 1.0, np.inf, np.nan, -1.0, 2.0, 1e-40, 4.0]]).astype(dt).reshape(r, c)
+    b = np.concatenate([(rng.random(r * c - 8) * 10 + 1.1), [2.0, 1.0, 2.0, 2.0, 2.0, 0.0, 10.0, np.inf]]).astype(dt).reshape(r, c)
+    X, B = nu.asarray(x, type=dt), nu.asarray(b, type=dt)
+    before = nu.launch_count()
+    got = nu.log(X, B)
+    assert nu.launch_count() - before == 1
+    want = nu.divide(nu.log(X), nu.log(B)).to_numpy()
+    assert same_bits(got.to_numpy(), want).all()
+    # broadcast base (a row vector) through the rows kernel, and :out
+    v = nu.asarray(b[0].copy(), type=dt)
+    out = nu.empty((r, c), X.element_type)
+    nu.log(X, v, out=out)
+    want = nu.divide(nu.log(X), nu.log(v)).to_numpy()
+    assert same_bits(out.to_numpy(), want).all()
+    with np.errstate(all="ignore"):
+        ref = np.log(x.astype(np.float64)) / np.log(b[0].astype(np.float64))
+    fin = np.isfinite(ref) & (np.abs(np.log(b[0].astype(np.float64))) > 0.05)
+    tol = 4 * np.finfo(dt).eps
+    assert np.allclose(out.to_numpy()[fin], ref[fin], rtol=tol, atol=0)
