@@ -21,6 +21,7 @@
 ;;; op codes (include/nuk.h)
 (defconstant +add+ 0) (defconstant +sub+ 1) (defconstant +mul+ 2) (defconstant +div+ 3)
 (defconstant +max+ 4) (defconstant +min+ 5) (defconstant +pow+ 6) (defconstant +atan2+ 7)
+(defconstant +logb+ 13) ; nu:log x y in one pass (replaces the log, log, divide of two-arg-fn-float.lisp:531-547)
 (defconstant +sum+ 0) (defconstant +hmax+ 1) (defconstant +hmin+ 2)
 
 (cffi:defcfun ("nuk_last_error" %last-error) :string)

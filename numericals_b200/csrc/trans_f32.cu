@@ -41,7 +41,10 @@ namespace nuk {
 #endif
 // measured on B200 (profiles/time_unroll_r01.txt, 2^28 elements): 4 packs per thread beat 1 by 15-30 % for
 // every unary below (tan 5.2 vs 4.2 TB/s, cosh 5.2 vs 4.0), 2 packs are best for the binary ones
-#define NUK_F32_VIA_F64(Name, FN) NUK_F32_UNARY_U(Name, FN, 4)
+#ifndef NUK_F32_UNROLL
+#define NUK_F32_UNROLL 4
+#endif
+#define NUK_F32_VIA_F64(Name, FN) NUK_F32_UNARY_U(Name, FN, NUK_F32_UNROLL)
 #define NUK_F32_BINARY(Name, FN)                        \
   struct Name {                                         \
     using In = float; using Out = float;                \
@@ -53,10 +56,10 @@ namespace nuk {
 NUK_F32_UNARY_FAST(SinF, sin_f32, 4, 8, NUK_FAST_TRIG32) NUK_F32_UNARY_FAST(CosF, cos_f32, 4, 8, NUK_FAST_TRIG32) NUK_F32_UNARY(TanhF, tanh_f32)
 NUK_F32_UNARY(LogF, log_f32)
 NUK_F32_UNARY_U(ExpF, exp_f32, 2)   // 5.9 TB/s with 2 packs per thread vs 5.2 with 4 (profiles/membench_r01.txt)
-NUK_F32_UNARY_FAST(TanF, tan_f32, 4, 0, NUK_FAST_TRIG32) NUK_F32_VIA_F64(AsinF, asin_f32) NUK_F32_VIA_F64(AcosF, acos_f32)
-NUK_F32_VIA_F64(AtanF, atan_f32) NUK_F32_UNARY_FAST(SinhF, sinh_f32, 4, 0, NUK_FAST_HYP32) NUK_F32_UNARY_FAST(CoshF, cosh_f32, 4, 0, NUK_FAST_HYP32)
-NUK_F32_UNARY_FAST(AsinhF, asinh_f32, 4, 0, NUK_FAST_HYP32) NUK_F32_UNARY_FAST(AcoshF, acosh_f32, 4, 0, NUK_FAST_HYP32)
-NUK_F32_UNARY_FAST(AtanhF, atanh_f32, 4, 0, NUK_FAST_HYP32)
+NUK_F32_UNARY_FAST(TanF, tan_f32, NUK_F32_UNROLL, 0, NUK_FAST_TRIG32) NUK_F32_VIA_F64(AsinF, asin_f32) NUK_F32_VIA_F64(AcosF, acos_f32)
+NUK_F32_VIA_F64(AtanF, atan_f32) NUK_F32_UNARY_FAST(SinhF, sinh_f32, NUK_F32_UNROLL, 0, NUK_FAST_HYP32) NUK_F32_UNARY_FAST(CoshF, cosh_f32, NUK_F32_UNROLL, 0, NUK_FAST_HYP32)
+NUK_F32_UNARY_FAST(AsinhF, asinh_f32, NUK_F32_UNROLL, 0, NUK_FAST_HYP32) NUK_F32_UNARY_FAST(AcoshF, acosh_f32, NUK_F32_UNROLL, 0, NUK_FAST_HYP32)
+NUK_F32_UNARY_FAST(AtanhF, atanh_f32, NUK_F32_UNROLL, 0, NUK_FAST_HYP32)
 struct Atan2F {
   using In = float; using Out = float;
   static constexpr int kArity = 2;

@@ -19,11 +19,14 @@ namespace nuk {
     static constexpr int kMapUnroll = 1;                \
     NUK_D double operator()(double a, double b) const { return nukmath::FN(a, b); } \
   };
+#ifndef NUK_F64_UNROLL
+#define NUK_F64_UNROLL 2
+#endif
 #define NUK_F64_UNARY_FAST(Name, FN, MINB, ON)           \
   struct Name {                                         \
     using In = double; using Out = double;              \
     static constexpr int kArity = 1;                    \
-    static constexpr int kMapUnroll = 2;                \
+    static constexpr int kMapUnroll = NUK_F64_UNROLL;   \
     static constexpr int kMapMinBlocks = MINB;          \
     static constexpr bool kHasFast = ON;                \
     NUK_D double operator()(double a) const { return nukmath::FN(a); } \
