@@ -71,6 +71,9 @@ template <class F> struct MapMinBlocks<F, std::void_t<decltype(F::kMapMinBlocks)
 // compiler interleaves the independent dependency chains of the elements (the per-element special-case
 // branches of operator() pin instruction-level parallelism at 1 and leave the kernel latency-bound at
 // the 40-50 % occupancy these register-heavy functions get) -- and re-does flagged elements afterwards.
+#ifndef NUK_ROWS_FAST
+#define NUK_ROWS_FAST 1   // the rows kernel takes the split too (A/B: tools/time_rows.py)
+#endif
 template <class F, class = void> struct HasFast { static constexpr bool value = false; };
 template <class F> struct HasFast<F, std::void_t<decltype(F::kHasFast)>> { static constexpr bool value = F::kHasFast; };
 template <class F> NUK_D typename F::Out apply_fast(const F &f, typename F::In a, typename F::In b, bool &slow) {
@@ -217,8 +220,18 @@ struct RowsDesc {
   int rows_per_cta;
 };
 
+// the rows kernel takes the split too (tools/time_rows.py: (8192 x 8192) ^ (8192) f32 0.314 -> 0.244 ms, f64 0.499 ->
+// 0.395 ms); a functor may override its unroll / register cap (kRowsUnroll, kRowsMinBlocks: atan2 f64 0.596 -> 0.458 ms)
+template <class F, class = void> struct RowsTuning {   // default: 4 packs per thread, registers uncapped
+  static constexpr int kUnroll = 4;
+  static constexpr int kMinBlocks = 0;
+};
+template <class F> struct RowsTuning<F, std::void_t<decltype(F::kRowsUnroll)>> {
+  static constexpr int kUnroll = F::kRowsUnroll;
+  static constexpr int kMinBlocks = F::kRowsMinBlocks;
+};
 template <class F, int UNROLL>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, RowsTuning<F>::kMinBlocks)
 k_map_rows(RowsDesc d, const typename F::In *x, const typename F::In *y, typename F::Out *out,
            Scalar64 xv, Scalar64 yv, F f) {
   using In = typename F::In;
@@ -293,11 +306,29 @@ k_map_rows(RowsDesc d, const typename F::In *x, const typename F::In *y, typenam
       const int64_t c = c0 + (int64_t)u * kThreads * E;
       if (full[u]) {
         POut rr;
+        if constexpr (HasFast<F>::value && NUK_ROWS_FAST) {
+          In av[E], bv[E];
+          bool slow[E], any = false;
 #pragma unroll
-        for (int e = 0; e < E; ++e) {
-          const In av = !x_col ? xs : (x_rowinv ? ha[u].v[e] : a[u].v[e]);
-          const In bv = (F::kArity == 2) ? (!y_col ? ys : (y_rowinv ? hb[u].v[e] : b[u].v[e])) : ys;
-          rr.v[e] = apply(f, av, bv);
+          for (int e = 0; e < E; ++e) {
+            av[e] = !x_col ? xs : (x_rowinv ? ha[u].v[e] : a[u].v[e]);
+            bv[e] = (F::kArity == 2) ? (!y_col ? ys : (y_rowinv ? hb[u].v[e] : b[u].v[e])) : ys;
+            slow[e] = false;
+            rr.v[e] = apply_fast(f, av[e], bv[e], slow[e]);
+            any |= slow[e];
+          }
+          if (any) {
+#pragma unroll
+            for (int e = 0; e < E; ++e)
+              if (slow[e]) rr.v[e] = apply(f, av[e], bv[e]);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < E; ++e) {
+            const In av = !x_col ? xs : (x_rowinv ? ha[u].v[e] : a[u].v[e]);
+            const In bv = (F::kArity == 2) ? (!y_col ? ys : (y_rowinv ? hb[u].v[e] : b[u].v[e])) : ys;
+            rr.v[e] = apply(f, av, bv);
+          }
         }
         st_stream(reinterpret_cast<POut *>(orow + c), rr);
       } else {
@@ -448,7 +479,8 @@ template <class F> int launch_map(const MapProblem &p, F f = F()) {
         d.ostride[1][a] = x ? p.sx[a] : 0;
         d.ostride[2][a] = (binary && y) ? p.sy[a] : 0;
       }
-      const int64_t col_tile = (int64_t)kThreads * UNROLL * E;
+      constexpr int RU = RowsTuning<F>::kUnroll;
+      const int64_t col_tile = (int64_t)kThreads * RU * E;
       const int64_t col_tiles = (d.ncols + col_tile - 1) / col_tile;
       // group rows so that the grid still covers the chip ~8x over
       const int64_t want_ctas = (int64_t)dev->sm_count * 8;
@@ -461,7 +493,7 @@ template <class F> int launch_map(const MapProblem &p, F f = F()) {
       const size_t gy = (size_t)row_groups * outer;
       if (col_tiles <= 65535 && gy <= 0x7fffffffu) {
         dim3 grid((unsigned)gy, (unsigned)col_tiles);
-        k_map_rows<F, UNROLL><<<grid, kThreads, 0, p.stream>>>(d, x, y, out, p.xv, p.yv, f);
+        k_map_rows<F, RU><<<grid, kThreads, 0, p.stream>>>(d, x, y, out, p.xv, p.yv, f);
         return post_launch("k_map_rows");
       }
     }

@@ -57,6 +57,7 @@ struct Atan2D {
   static constexpr int kArity = 2;
   static constexpr int kMapUnroll = 1;
   static constexpr int kMapMinBlocks = 5;
+  static constexpr int kRowsUnroll = 1, kRowsMinBlocks = 5;
   static constexpr bool kHasFast = NUK_FAST_INV64;
   NUK_D double operator()(double a, double b) const { return nukmath::atan2_f64(a, b); }
   NUK_D double fast(double a, double b, bool &slow) const { return nukmath::atan2_f64_fast(a, b, slow); }
