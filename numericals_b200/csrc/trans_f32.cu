@@ -91,7 +91,14 @@ struct LogbF {
   using In = float; using Out = float;
   static constexpr int kArity = 2;
   static constexpr int kMapUnroll = 2;
+  static constexpr bool kHasFast = true;
   NUK_D float operator()(float a, float b) const { return nukmath::log_f32(a) / nukmath::log_f32(b); }
+  NUK_D float fast(float a, float b, bool &slow) const {
+    bool sa, sb;
+    const float la = nukmath::log_f32_fast(a, sa), lb = nukmath::log_f32_fast(b, sb);
+    slow = sa | sb;
+    return la / lb;
+  }
 };
 
 int launch_trans_f32(int op, int arity, const MapProblem &p) {

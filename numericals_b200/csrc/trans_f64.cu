@@ -138,7 +138,14 @@ struct LogbD : TabLog {
   using In = double; using Out = double;
   static constexpr int kArity = 2;
   static constexpr int kMapUnroll = 2;
+  static constexpr bool kHasFast = true;
   NUK_D double operator()(double a, double b) const { return nukmath::log_f64(a, tab) / nukmath::log_f64(b, tab); }
+  NUK_D double fast(double a, double b, bool &slow) const {
+    bool sa, sb;
+    const double la = nukmath::log_f64_fast(a, tab, sa), lb = nukmath::log_f64_fast(b, tab, sb);
+    slow = sa | sb;
+    return la / lb;
+  }
 };
 
 int launch_trans_f64(int op, int arity, const MapProblem &p) {
