@@ -1,9 +1,13 @@
 // map.cuh -- the three elementwise kernels of libnuk and their launcher.
 //
-//   k_map_flat : everything contiguous (or scalar).  Persistent grid-stride over tiles of
-//                kThreads*UNROLL packs; one pack = 16 bytes of the widest operand type,
-//                all loads of a tile issued before the first use (UNROLL independent
-//                128-bit requests per operand per thread in flight), streaming stores.
+//   k_map_flat : everything contiguous (or scalar).  ONE tile of kThreads*UNROLL packs per CTA (the
+//                hardware CTA scheduler spreads tiles over the HBM channels better than a persistent
+//                grid-stride loop: 6.8 vs 5.9 TB/s, profiles/membench_r01.txt); one pack = 16 bytes of
+//                the widest operand type, all loads of a tile issued before the first use (UNROLL
+//                independent 128-bit requests per operand per thread in flight), streaming stores.
+//                Functor traits: kMapUnroll, kMapMinBlocks (register cap), kSmemBytes + stage() (lookup
+//                tables copied into shared memory once per CTA, after the operand loads are issued),
+//                kHasFast + fast() (branch-free main path for the whole pack, flagged elements re-done).
 //   k_map_rows : inner axis contiguous for OUT, inputs contiguous or broadcast (stride 0)
 //                along it; outer axes arbitrary.  A CTA owns a column tile x a group of
 //                consecutive rows; an operand that does not vary with the row (row-vector
