@@ -123,6 +123,8 @@ def hexd(x):
 def main():
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "numericals_b200", "csrc",
                        "nukmath_tables.inc")
+    if len(sys.argv) > 1:          # gen_tables.py OUT: write somewhere else (tests/test_tables_host.py)
+        out = sys.argv[1]
     lt, rmin, rmax = log_table()
     et = exp_table()
     # log1p(r) = r - r^2/2 + r^3 (B0 + B1 r + ... + B5 r^5) on [rmin, rmax]; error relative to r
