@@ -80,6 +80,9 @@ template <class F> struct MapMinBlocks<F, std::void_t<decltype(F::kMapMinBlocks)
 #endif
 template <class F, class = void> struct HasFast { static constexpr bool value = false; };
 template <class F> struct HasFast<F, std::void_t<decltype(F::kHasFast)>> { static constexpr bool value = F::kHasFast; };
+// ... and may keep the per-element form for its scalar-operand tiles (kScalarSplit = false: pow f32 spills there)
+template <class F, class = void> struct ScalarSplit { static constexpr bool value = true; };
+template <class F> struct ScalarSplit<F, std::void_t<decltype(F::kScalarSplit)>> { static constexpr bool value = F::kScalarSplit; };
 template <class F> NUK_D typename F::Out apply_fast(const F &f, typename F::In a, typename F::In b, bool &slow) {
   if constexpr (F::kArity == 2) return f.fast(a, b, slow);
   else return f.fast(a, slow);
@@ -91,7 +94,11 @@ template <class F> NUK_D typename F::Out apply(const F &f, typename F::In a, typ
 }
 
 // ------------------------------------------------------------------ flat kernel
-template <class F, int UNROLL>
+// MODE: 2 = one kernel for all-vector and scalar-operand tiles (default); a split functor is instantiated twice,
+// 0 = all-vector tiles only, 1 = scalar-operand tiles only, so that each gets its own register allocation (with
+// both branches in one kernel the split of the scalar branch spilled and slowed the vector path: pow f64 1.13 ->
+// 1.41 ms, profiles/fast_split_ab_r01.txt).
+template <class F, int UNROLL, int MODE = 2>
 __global__ void __launch_bounds__(kThreads, MapMinBlocks<F>::value)
 k_map_flat(size_t n, const typename F::In *x, const typename F::In *y, typename F::Out *out,
            int x_scalar, int y_scalar, Scalar64 xv, Scalar64 yv, F f) {
@@ -116,7 +123,7 @@ k_map_flat(size_t n, const typename F::In *x, const typename F::In *y, typename 
   // ONE tile per CTA (grid = nfull + 1): on B200 the hardware CTA scheduler spreads the tiles over
   // the HBM channels better than a persistent grid-stride loop does -- 6.8 vs 5.9 TB/s for a unary
   // f32 map, profiles/membench_r01.txt -- so the "grid-stride" loop degenerates to one iteration.
-  if (blockIdx.x < nfull && !x_scalar && (F::kArity == 1 || !y_scalar)) {
+  if (MODE != 1 && blockIdx.x < nfull && (MODE == 0 || (!x_scalar && (F::kArity == 1 || !y_scalar)))) {
     // all-vector tile (the hot case): no per-element scalar selects
     const size_t base = (size_t)blockIdx.x * kTile + threadIdx.x;
     PIn a[UNROLL], b[UNROLL];
@@ -156,7 +163,7 @@ k_map_flat(size_t n, const typename F::In *x, const typename F::In *y, typename 
       }
       st_stream(op + base + (size_t)u * kThreads, r);
     }
-  } else if (blockIdx.x < nfull) {
+  } else if (MODE != 0 && blockIdx.x < nfull) {
     // a scalar operand (uniform across the grid): same tile with broadcast values
     stage_tables(f);
     const size_t base = (size_t)blockIdx.x * kTile + threadIdx.x;
@@ -182,6 +189,22 @@ k_map_flat(size_t n, const typename F::In *x, const typename F::In *y, typename 
 #pragma unroll
         for (int w = 0; w < 4; ++w) wr[w] = Word4<F>::op(wa[w], wb[w]);
         memcpy(&r, wr, 16);
+      } else if constexpr (HasFast<F>::value && MODE == 1 && ScalarSplit<F>::value) {
+        In av[E], bv[E];
+        bool slow[E], any = false;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          av[e] = x_scalar ? xs : a[u].v[e];
+          bv[e] = (F::kArity == 2 && !y_scalar) ? b[u].v[e] : ys;
+          slow[e] = false;
+          r.v[e] = apply_fast(f, av[e], bv[e], slow[e]);
+          any |= slow[e];
+        }
+        if (any) {
+#pragma unroll
+          for (int e = 0; e < E; ++e)
+            if (slow[e]) r.v[e] = apply(f, av[e], bv[e]);
+        }
       } else {
 #pragma unroll
         for (int e = 0; e < E; ++e)
@@ -444,8 +467,16 @@ template <class F> int launch_map(const MapProblem &p, F f = F()) {
         set_error(NUK_ERR_INVALID, "array too large for one launch (%zu tiles)", nfull);
         return NUK_ERR_INVALID;
       }
-      k_map_flat<F, FU><<<(unsigned)(nfull + 1), kThreads, 0, p.stream>>>(n, x, y, out, xs ? 1 : 0,
-                                                                       ys ? 1 : 0, p.xv, p.yv, f);
+      if constexpr (HasFast<F>::value && F::kArity == 2) {
+        if (xs || ys)
+          k_map_flat<F, FU, 1><<<(unsigned)(nfull + 1), kThreads, 0, p.stream>>>(n, x, y, out, xs ? 1 : 0, ys ? 1 : 0,
+                                                                            p.xv, p.yv, f);
+        else
+          k_map_flat<F, FU, 0><<<(unsigned)(nfull + 1), kThreads, 0, p.stream>>>(n, x, y, out, 0, 0, p.xv, p.yv, f);
+      } else {
+        k_map_flat<F, FU><<<(unsigned)(nfull + 1), kThreads, 0, p.stream>>>(n, x, y, out, xs ? 1 : 0,
+                                                                         ys ? 1 : 0, p.xv, p.yv, f);
+      }
       return post_launch("k_map_flat");
     }
   }
