@@ -98,8 +98,12 @@ template <class F> NUK_D typename F::Out apply(const F &f, typename F::In a, typ
 // 0 = all-vector tiles only, 1 = scalar-operand tiles only, so that each gets its own register allocation (with
 // both branches in one kernel the split of the scalar branch spilled and slowed the vector path: pow f64 1.13 ->
 // 1.41 ms, profiles/fast_split_ab_r01.txt).
+template <class F, class = void> struct ScalarMinBlocks { static constexpr int value = MapMinBlocks<F>::value; };
+template <class F> struct ScalarMinBlocks<F, std::void_t<decltype(F::kScalarMinBlocks)>> {
+  static constexpr int value = F::kScalarMinBlocks;   // register cap of the MODE 1 instantiation
+};
 template <class F, int UNROLL, int MODE = 2>
-__global__ void __launch_bounds__(kThreads, MapMinBlocks<F>::value)
+__global__ void __launch_bounds__(kThreads, MODE == 1 ? ScalarMinBlocks<F>::value : MapMinBlocks<F>::value)
 k_map_flat(size_t n, const typename F::In *x, const typename F::In *y, typename F::Out *out,
            int x_scalar, int y_scalar, Scalar64 xv, Scalar64 yv, F f) {
   using In = typename F::In;

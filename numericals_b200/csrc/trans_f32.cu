@@ -81,7 +81,14 @@ struct PowF : TabPowF {   // 640 bytes of tables in shared memory (nukmath_tab.c
   static constexpr int kMapUnroll = NUK_POWF_UNROLL;
   static constexpr int kMapMinBlocks = NUK_POWF_MINB;
   static constexpr bool kHasFast = true;
-  static constexpr bool kScalarSplit = false;   // nu:expt x 2.5: 0.70 ms per 2^28 per-element, 0.98 ms split (spills at 48 registers)
+#ifndef NUK_POWF_SCALAR_SPLIT
+#define NUK_POWF_SCALAR_SPLIT false
+#endif
+#ifndef NUK_POWF_SCALAR_MINB
+#define NUK_POWF_SCALAR_MINB 0   // uncapped, per-element: 0.68 ms; split at 64 / 80 registers 0.71 / 0.79 ms
+#endif
+  static constexpr bool kScalarSplit = NUK_POWF_SCALAR_SPLIT;   // nu:expt x 2.5: 0.70 ms per 2^28 per-element, 0.98 ms split at 48 registers (spills)
+  static constexpr int kScalarMinBlocks = NUK_POWF_SCALAR_MINB;
   NUK_D float operator()(float a, float b) const { return nukmath::pow_f32(a, b, tab); }
   NUK_D float fast(float a, float b, bool &slow) const { return nukmath::pow_f32_fast(a, b, tab, slow); }
 };
