@@ -163,3 +163,22 @@ def test_two_arg_log_is_one_pass_with_the_bits_of_three(dt, nu):
     fin = np.isfinite(ref) & (np.abs(np.log(b[0].astype(np.float64))) > 0.05)
     tol = 4 * np.finfo(dt).eps
     assert np.allclose(out.to_numpy()[fin], ref[fin], rtol=tol, atol=0)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_scalar_polymorphs_of_split_functors(dt, nu):
+    """nu:expt x c / nu:expt c x / atan2 x c run the MODE 1 instantiation of the flat kernel (scalar-operand tiles,
+    two-arg-fn-float.lisp:238-294): same bits as the all-vector kernel on a filled array, specials included"""
+    rng = np.random.default_rng(12)
+    n = (1 << 18) + 37
+    x = scatter((rng.random(n) * 6 - 1).astype(dt), specials(dt), rng)
+    X = nu.asarray(x, type=dt)
+    for c in (2.5, -0.5, 3.0, 0.0):
+        C_ = nu.asarray(np.full(n, c, dtype=dt), type=dt)
+        for name, fn in (("expt", nu.expt), ("atan2", nu.atan2)):
+            a = fn(X, c).to_numpy()
+            b = fn(X, C_).to_numpy()
+            assert same_bits(a, b).all(), (name, "x c", c)
+            a = fn(c, X).to_numpy()
+            b = fn(C_, X).to_numpy()
+            assert same_bits(a, b).all(), (name, "c x", c)
