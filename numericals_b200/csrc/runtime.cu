@@ -98,7 +98,7 @@ static std::unordered_map<std::string, long> &options() {
   static std::unordered_map<std::string, long> o = [] {
     std::unordered_map<std::string, long> m;
     m["grid_mult"] = 8;        // resident CTAs per SM targeted by persistent map kernels
-    m["reduce_grid_mult"] = 8; // CTAs per SM in pass 1 of full reductions
+    m["reduce_grid_mult"] = 16; // CTAs per SM in pass 1 of full reductions (16: sum/max f32/f64 +7 % over 8, profiles/reduce_grid_r01.txt)
     m["stage_mb"] = 32;        // chunk size of the host-pointer staging pipeline
     m["stage_slots"] = 3;
     m["col_split_rows"] = 256; // rows per CTA in the split column reduction
