@@ -131,13 +131,34 @@ int nuk_host_free(void *hptr);
 int nuk_host_register(void *hptr, size_t bytes); /* pin an existing buffer (e.g. a Lisp vector) */
 int nuk_host_unregister(void *hptr);
 int nuk_pointer_is_device(const void *p);        /* 1 device/managed, 0 host */
+/* How BMAS_* symbols decide where an operand lives (thread-local).  NUK_PTR_AUTO asks the driver for
+ * every pointer; NUK_PTR_DEVICE is for a host layer that keeps its arrays in device storage
+ * (dense-arrays device backend): operands with a non-zero stride are device pointers by contract and
+ * no driver query is made (a stride-0 operand may still be the reference's 1-element host scalar,
+ * src/basic-math/two-arg-fn-non-comparison.lisp:226-232). */
+enum { NUK_PTR_AUTO = 0, NUK_PTR_DEVICE = 1 };
+int nuk_set_pointer_mode(int mode);
+int nuk_get_pointer_mode(void);
+/* number of host mover threads that stage pageable / strided host operands of BMAS_* calls
+ * (option "stage_threads" / NUK_STAGE_THREADS, read when the pool starts; 0 = half the cores, at most 8) */
+int nuk_host_mover_threads(void);
 int nuk_flush_l2(nuk_stream_t s);                /* writes a > L2-sized scratch buffer (benchmark hygiene) */
 /* diagnostic: counts float bit patterns in [lo_bits, hi_bits) for which the MUFU-seeded reciprocal /
    square root used inside the transcendental kernels differ from rcp.rn.f32 / sqrt.rn.f32 (expected 0
    over the normal range 2^-100 .. 2^100); synchronous */
 int nuk_selftest_seeds(uint32_t lo_bits, uint32_t hi_bits, unsigned long long *mismatches, nuk_stream_t s);
 
-/* knobs (also readable from the environment at first use: NUK_GRID_MULT, NUK_STAGE_MB) */
+/* CUDA-graph replay of a launch-bound call sequence (C1: 10^6-element maps).  Capture on a stream
+ * made by nuk_stream_create after one warm-up pass of the same calls; maps and axis reductions are
+ * capture-safe, value-returning BMAS reductions (they synchronise) are not. */
+typedef void *nuk_graph_t;
+int nuk_graph_begin(nuk_stream_t s);
+int nuk_graph_end(nuk_stream_t s, nuk_graph_t *g);
+int nuk_graph_launch(nuk_graph_t g, nuk_stream_t s);
+int nuk_graph_destroy(nuk_graph_t g);
+
+/* knobs (also readable from the environment at first use: NUK_GRID_MULT, NUK_STAGE_MB, ...).
+ * NUK_LOG=1 in the environment prints one line per kernel launch to stderr. */
 int nuk_set_option(const char *name, long value);
 long nuk_get_option(const char *name);
 /* number of kernels launched by this library since load (all threads) */

@@ -83,6 +83,9 @@ def _declare(L):
         "nuk_host_alloc": [C.POINTER(_vp), C.c_size_t], "nuk_host_free": [_vp],
         "nuk_host_register": [_vp, C.c_size_t], "nuk_host_unregister": [_vp],
         "nuk_pointer_is_device": [_vp], "nuk_flush_l2": [_vp],
+        "nuk_set_pointer_mode": [C.c_int], "nuk_get_pointer_mode": [], "nuk_host_mover_threads": [],
+        "nuk_graph_begin": [_vp], "nuk_graph_end": [_vp, C.POINTER(_vp)], "nuk_graph_launch": [_vp, _vp],
+        "nuk_graph_destroy": [_vp],
         "nuk_map1": [C.c_int, C.c_int, C.c_int, _i64p, _i64p, _i64p, _vp, _vp, _vp],
         "nuk_map2": [C.c_int, C.c_int, C.c_int, _i64p, _i64p, _i64p, _i64p, _vp, _vp, _vp, _vp],
         "nuk_cmp2": [C.c_int, C.c_int, C.c_int, _i64p, _i64p, _i64p, _i64p, _vp, _vp, _vp, _vp],

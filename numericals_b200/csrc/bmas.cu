@@ -9,109 +9,9 @@
 // complete, which is the reference's synchronous contract.  There is no CPU compute path.
 #include <vector>
 #include "dispatch.cuh"
+#include "staging.cuh"
 
 namespace nuk {
-
-enum PtrKind { PK_NULL = 0, PK_DEVICE = 1, PK_HOST = 2 };
-static PtrKind classify(const void *p) {
-  if (!p) return PK_NULL;
-  cudaPointerAttributes a;
-  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
-    cudaGetLastError();
-    return PK_HOST;
-  }
-  return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? PK_DEVICE : PK_HOST;
-}
-
-// ------------------------------------------------------------------ staging pipeline
-struct Stager {
-  static constexpr int kMaxSlots = 4;
-  int nslots = 0;
-  size_t cap = 0;                       // bytes per operand buffer
-  cudaStream_t streams[kMaxSlots] = {};
-  void *buf[kMaxSlots][3] = {};         // [slot][x, y, out]
-  cudaEvent_t entry = nullptr;
-  int device = -1;
-  ~Stager() { release(); }
-  void release() {
-    for (int s = 0; s < nslots; ++s) {
-      for (int o = 0; o < 3; ++o)
-        if (buf[s][o]) cudaFree(buf[s][o]);
-      if (streams[s]) cudaStreamDestroy(streams[s]);
-    }
-    if (entry) cudaEventDestroy(entry);
-    nslots = 0; cap = 0; entry = nullptr;
-    memset(buf, 0, sizeof(buf));
-    memset(streams, 0, sizeof(streams));
-  }
-  int ensure(size_t want_cap, int want_slots, int dev) {
-    if (want_slots > kMaxSlots) want_slots = kMaxSlots;
-    if (want_slots < 1) want_slots = 1;
-    if (nslots == want_slots && cap >= want_cap && device == dev) return NUK_OK;
-    release();
-    device = dev;
-    for (int s = 0; s < want_slots; ++s) {
-      NUK_CUDA(cudaStreamCreateWithFlags(&streams[s], cudaStreamNonBlocking));
-      for (int o = 0; o < 3; ++o) NUK_CUDA(cudaMalloc(&buf[s][o], want_cap));
-      nslots = s + 1;
-    }
-    NUK_CUDA(cudaEventCreateWithFlags(&entry, cudaEventDisableTiming));
-    cap = want_cap;
-    return NUK_OK;
-  }
-};
-static thread_local Stager tl_stager;
-
-// one operand of a BMAS-shaped (rank-1) call
-struct Opnd {
-  const void *ptr;
-  long inc;
-  size_t size;     // element size
-  PtrKind kind;
-};
-
-// copy `m` elements starting at logical index c0 of a HOST strided operand into a contiguous
-// device buffer (in ADDRESS order); returns the device pointer/inc that walk it in logical order
-static int stage_in(const Opnd &o, long c0, long m, void *dbuf, cudaStream_t st, const void **dptr,
-                    long *dinc) {
-  const char *base = static_cast<const char *>(o.ptr);
-  if (o.inc == 1) {
-    NUK_CUDA(cudaMemcpyAsync(dbuf, base + (size_t)c0 * o.size, (size_t)m * o.size,
-                             cudaMemcpyHostToDevice, st));
-    *dptr = dbuf; *dinc = 1;
-  } else if (o.inc == -1) {
-    const char *lo = base + (int64_t)(c0 + m - 1) * o.inc * (int64_t)o.size;
-    NUK_CUDA(cudaMemcpyAsync(dbuf, lo, (size_t)m * o.size, cudaMemcpyHostToDevice, st));
-    *dptr = static_cast<char *>(dbuf) + (size_t)(m - 1) * o.size; *dinc = -1;
-  } else {
-    const long ainc = o.inc < 0 ? -o.inc : o.inc;
-    const char *lo = o.inc > 0 ? base + (int64_t)c0 * o.inc * (int64_t)o.size
-                               : base + (int64_t)(c0 + m - 1) * o.inc * (int64_t)o.size;
-    NUK_CUDA(cudaMemcpy2DAsync(dbuf, o.size, lo, (size_t)ainc * o.size, o.size, (size_t)m,
-                               cudaMemcpyHostToDevice, st));
-    if (o.inc > 0) { *dptr = dbuf; *dinc = 1; }
-    else { *dptr = static_cast<char *>(dbuf) + (size_t)(m - 1) * o.size; *dinc = -1; }
-  }
-  return NUK_OK;
-}
-static int stage_out(const Opnd &o, long c0, long m, const void *dbuf, cudaStream_t st) {
-  char *base = static_cast<char *>(const_cast<void *>(o.ptr));
-  if (o.inc == 1) {
-    NUK_CUDA(cudaMemcpyAsync(base + (size_t)c0 * o.size, dbuf, (size_t)m * o.size,
-                             cudaMemcpyDeviceToHost, st));
-  } else if (o.inc == -1) {
-    char *lo = base + (int64_t)(c0 + m - 1) * o.inc * (int64_t)o.size;
-    NUK_CUDA(cudaMemcpyAsync(lo, dbuf, (size_t)m * o.size, cudaMemcpyDeviceToHost, st));
-  } else {
-    const long ainc = o.inc < 0 ? -o.inc : o.inc;
-    char *lo = o.inc > 0 ? base + (int64_t)c0 * o.inc * (int64_t)o.size
-                         : base + (int64_t)(c0 + m - 1) * o.inc * (int64_t)o.size;
-    // only the view's elements are written (test-definition-macros.lisp:86-99)
-    NUK_CUDA(cudaMemcpy2DAsync(lo, (size_t)ainc * o.size, dbuf, o.size, o.size, (size_t)m,
-                               cudaMemcpyDeviceToHost, st));
-  }
-  return NUK_OK;
-}
 
 static void host_scalar(const Opnd &o, Scalar64 *v) {
   memset(v, 0, sizeof(*v));
@@ -129,11 +29,11 @@ static int run_map_1d(int arity, long n, Opnd x, Opnd y, Opnd out, Launch launch
     set_error(NUK_ERR_INVALID, "OUT stride 0 with n > 1");
     return NUK_ERR_INVALID;
   }
-  x.kind = classify(x.ptr);
-  y.kind = arity == 2 ? classify(y.ptr) : PK_NULL;
-  out.kind = classify(out.ptr);
-  const bool any_host_array = (x.kind == PK_HOST && x.inc != 0) || (y.kind == PK_HOST && y.inc != 0) ||
-                              out.kind == PK_HOST;
+  x.kind = classify_ptr(x.ptr, x.inc != 0);
+  y.kind = arity == 2 ? classify_ptr(y.ptr, y.inc != 0) : PK_NULL;
+  out.kind = classify_ptr(out.ptr, true);
+  const bool any_host_array = (on_host(x.kind) && x.inc != 0) || (on_host(y.kind) && y.inc != 0) ||
+                              on_host(out.kind);
   const int64_t dims[1] = {n};
 
   if (!any_host_array) {
@@ -143,21 +43,20 @@ static int run_map_1d(int arity, long n, Opnd x, Opnd y, Opnd out, Launch launch
     const void *xp = x.ptr, *yp = arity == 2 ? y.ptr : nullptr;
     Scalar64 xv, yv;
     memset(&xv, 0, sizeof(xv)); memset(&yv, 0, sizeof(yv));
-    if (x.kind == PK_HOST) { host_scalar(x, &xv); xp = nullptr; }
-    if (arity == 2 && y.kind == PK_HOST) { host_scalar(y, &yv); yp = nullptr; }
+    if (on_host(x.kind)) { host_scalar(x, &xv); xp = nullptr; }
+    if (arity == 2 && on_host(y.kind)) { host_scalar(y, &yv); yp = nullptr; }
     NUK_TRY(make_problem(&p, arity, x.size, out.size, 1, dims, sx, sy, so, xp, yp,
                          const_cast<void *>(out.ptr), current_stream()));
     p.xv = xv; p.yv = yv;
     return launch(p);
   }
 
-  // ---- staged
+  // ---- staged (staging.cuh): chunk k on slot k mod S
   const size_t wide = x.size > out.size ? x.size : out.size;
-  size_t cap = (size_t)(option("stage_mb") > 0 ? option("stage_mb") : 32) << 20;
-  if ((size_t)n * wide < cap) cap = (((size_t)n * wide + 255) / 256) * 256;
+  const size_t cap = stage_chunk_bytes((size_t)n * wide);
   const long chunk = (long)(cap / wide);
-  Stager &sg = tl_stager;
-  NUK_TRY(sg.ensure(cap, (int)option("stage_slots"), dev->device));
+  Stager &sg = thread_stager();
+  NUK_TRY(sg.ensure(cap, (int)opt(OPT_STAGE_SLOTS), dev->device));
   // operands already on the device may still be in flight on the caller's stream
   NUK_CUDA(cudaEventRecord(sg.entry, current_stream()));
   for (int s = 0; s < sg.nslots; ++s) NUK_CUDA(cudaStreamWaitEvent(sg.streams[s], sg.entry, 0));
@@ -168,18 +67,20 @@ static int run_map_1d(int arity, long n, Opnd x, Opnd y, Opnd out, Launch launch
     const long m = (n - c0 < chunk) ? (n - c0) : chunk;
     const int slot = k % sg.nslots;
     cudaStream_t st = sg.streams[slot];
+    status = sg.begin_slot(slot);
+    if (status != NUK_OK) break;
     const void *xp = nullptr, *yp = nullptr;
     long xi = 0, yi = 0;
     Scalar64 xv, yv;
     memset(&xv, 0, sizeof(xv)); memset(&yv, 0, sizeof(yv));
     auto prep = [&](const Opnd &o, int which, const void **dp, long *di, Scalar64 *v) -> int {
       if (o.inc == 0) {
-        if (o.kind == PK_HOST) { host_scalar(o, v); *dp = nullptr; }
+        if (on_host(o.kind)) { host_scalar(o, v); *dp = nullptr; }
         else *dp = o.ptr;
         *di = 0;
         return NUK_OK;
       }
-      if (o.kind == PK_HOST) return stage_in(o, c0, m, sg.buf[slot][which], st, dp, di);
+      if (on_host(o.kind)) return sg.in(slot, which, o, c0, m, dp, di);
       *dp = static_cast<const char *>(o.ptr) + (int64_t)c0 * o.inc * (int64_t)o.size;
       *di = o.inc;
       return NUK_OK;
@@ -189,10 +90,8 @@ static int run_map_1d(int arity, long n, Opnd x, Opnd y, Opnd out, Launch launch
     if (status != NUK_OK) break;
     void *op;
     long oi;
-    if (out.kind == PK_HOST) {
-      // staged OUT is contiguous in address order; walk it in the logical direction
-      op = out.inc > 0 ? sg.buf[slot][2] : static_cast<char *>(sg.buf[slot][2]) + (size_t)(m - 1) * out.size;
-      oi = out.inc > 0 ? 1 : -1;
+    if (on_host(out.kind)) {
+      sg.out_target(slot, out, m, &op, &oi);
     } else {
       op = static_cast<char *>(const_cast<void *>(out.ptr)) + (int64_t)c0 * out.inc * (int64_t)out.size;
       oi = out.inc;
@@ -203,64 +102,49 @@ static int run_map_1d(int arity, long n, Opnd x, Opnd y, Opnd out, Launch launch
     if (status != NUK_OK) break;
     p.xv = xv; p.yv = yv;
     status = launch(p);
-    if (status == NUK_OK && out.kind == PK_HOST) status = stage_out(out, c0, m, sg.buf[slot][2], st);
+    if (status == NUK_OK && on_host(out.kind)) status = sg.out(slot, out, c0, m);
   }
-  for (int s = 0; s < sg.nslots; ++s) {
-    cudaError_t e = cudaStreamSynchronize(sg.streams[s]);
-    if (e != cudaSuccess && status == NUK_OK) status = cuda_fail(e, "staging stream sync", __FILE__, __LINE__);
-  }
-  return status;
+  const int fin = sg.finish_all();
+  return status != NUK_OK ? status : fin;
 }
 
 // ------------------------------------------------------------------ reductions by value
 static int reduce_value(int red, int dtype, long n, const void *x, long incx, void *result) {
   nuk_clear_error();
+  const size_t sz = dtype_size(dtype);
+  memset(result, 0, sz);   // a defined value even when the call fails (BMAS returns by value, no error channel)
   const DeviceInfo *dev = device_info();
   if (!dev) return nuk_last_status();
-  const size_t sz = dtype_size(dtype);
-  memset(result, 0, sz);
   if (n <= 0) return NUK_OK;
   cudaStream_t st = current_stream();
   void *pin = nullptr, *dres = nullptr;
   NUK_TRY(pinned_slot(&pin));
-  const PtrKind kind = classify(x);
+  const PtrKind kind = classify_ptr(x, incx != 0);
   if (kind == PK_DEVICE) {
-    // scratch layout: [0,64) result, then the reduction's own partials (separate arena call)
-    static thread_local void *dslot = nullptr;
-    if (!dslot) NUK_CUDA(cudaMalloc(&dslot, 64));
-    dres = dslot;
+    NUK_TRY(thread_buffer(BUF_RESULT, 64, &dres));
     NUK_TRY(reduce_1d_device(red, dtype, (size_t)n, x, incx, dres, st));
   } else {
     // host operand: stage chunk by chunk, one partial per chunk, fixed-order combine on device
-    size_t cap = (size_t)(option("stage_mb") > 0 ? option("stage_mb") : 32) << 20;
-    if ((size_t)n * sz < cap) cap = (((size_t)n * sz + 255) / 256) * 256;
+    const size_t cap = stage_chunk_bytes((size_t)n * sz);
     const long chunk = (long)(cap / sz);
     const long nchunks = (n + chunk - 1) / chunk;
-    Stager &sg = tl_stager;
-    NUK_TRY(sg.ensure(cap, (int)option("stage_slots"), dev->device));
-    static thread_local void *dpart = nullptr;
-    static thread_local size_t dpart_cap = 0;
-    if (dpart_cap < (size_t)(nchunks + 8) * 8) {
-      if (dpart) cudaFree(dpart);
-      dpart_cap = (size_t)(nchunks + 8) * 8;
-      NUK_CUDA(cudaMalloc(&dpart, dpart_cap));
-    }
-    Opnd o{x, incx, sz, PK_HOST};
+    Stager &sg = thread_stager();
+    NUK_TRY(sg.ensure(cap, (int)opt(OPT_STAGE_SLOTS), dev->device));
+    void *dpart = nullptr;
+    NUK_TRY(thread_buffer(BUF_PARTS, (size_t)(nchunks + 8) * 8, &dpart));
+    Opnd o{x, incx, sz, kind};
     long c0 = 0;
     for (long k = 0; c0 < n; ++k, c0 += chunk) {
       const long m = (n - c0 < chunk) ? (n - c0) : chunk;
       const int slot = (int)(k % sg.nslots);
       const void *dp;
       long di;
-      if (incx == 0) {
-        set_error(NUK_ERR_INVALID, "reduction over a stride-0 host operand");
-        return NUK_ERR_INVALID;
-      }
-      NUK_TRY(stage_in(o, c0, m, sg.buf[slot][0], sg.streams[slot], &dp, &di));
+      NUK_TRY(sg.begin_slot(slot));
+      NUK_TRY(sg.in(slot, 0, o, c0, m, &dp, &di));
       NUK_TRY(reduce_1d_device(red, dtype, (size_t)m, dp, di, static_cast<char *>(dpart) + k * sz,
-                               sg.streams[slot]));
+                               sg.streams[slot], k == 0 ? 0 : NUK_REDUCE_NO_SEED));
     }
-    for (int s = 0; s < sg.nslots; ++s) NUK_CUDA(cudaStreamSynchronize(sg.streams[s]));
+    NUK_TRY(sg.finish_all());
     dres = static_cast<char *>(dpart) + nchunks * sz;
     const int red2 = (red == NUK_SUMSQ) ? NUK_SUM : red;
     NUK_TRY(reduce_1d_device(red2, dtype, (size_t)nchunks, dpart, 1, dres, st));

@@ -36,13 +36,29 @@ struct DeviceInfo {
 const DeviceInfo *device_info();      // current device of this thread (lazy init); nullptr + error if none
 cudaStream_t current_stream();        // thread-local stream used by BMAS_* symbols
 void count_launch(unsigned n = 1);    // gpu_launches bookkeeping
-long option(const char *name);        // NUK_* knobs
-int post_launch(const char *kernel);  // cudaGetLastError -> status
+int post_launch(const char *kernel);  // cudaGetLastError -> status (+ the NUK_LOG per-launch line)
 
-// scratch memory private to (thread, stream): reduction partials etc.
+// NUK_* knobs: lock-free reads on the launch path (nuk_set_option / the environment write them)
+enum Opt {
+  OPT_GRID_MULT = 0, OPT_REDUCE_GRID_MULT, OPT_STAGE_MB, OPT_STAGE_SLOTS, OPT_COL_SPLIT_ROWS, OPT_SEQ_COLS,
+  OPT_STAGE_THREADS, OPT_ROWS_CTAS_PER_SM, OPT_COUNT
+};
+long opt(Opt o);
+
+// pointer classification of a BMAS_* operand.  NUK_PTR_AUTO asks the driver (cudaPointerGetAttributes);
+// in NUK_PTR_DEVICE mode (nuk_set_pointer_mode: the dense-arrays device-storage backend knows where its
+// arrays live) strided operands are taken as device pointers without a driver call.
+enum PtrKind { PK_NULL = 0, PK_DEVICE = 1, PK_HOST = 2 /* page-locked */, PK_PAGEABLE = 3 };
+PtrKind classify_ptr(const void *p, bool strided);
+inline bool on_host(PtrKind k) { return k == PK_HOST || k == PK_PAGEABLE; }
+
+// scratch memory private to (thread, device, stream): reduction partials etc.
 int scratch(cudaStream_t s, size_t bytes, void **dptr);
-// pinned result slot private to the thread (8 * 64 bytes)
+// pinned result slot private to the thread (8 * 64 bytes, portable across devices)
 int pinned_slot(void **hptr);
+// small device buffers private to (thread, current device, slot), grown on demand
+enum BufSlot { BUF_RESULT = 0, BUF_PARTS, BUF_HS_X, BUF_HS_Y, BUF_COUNT };
+int thread_buffer(BufSlot slot, size_t bytes, void **dptr);
 
 // grid size for a persistent / grid-stride kernel: min(work_blocks, sm_count * mult)
 int grid_for(size_t work_blocks, int blocks_per_sm);

@@ -40,8 +40,10 @@ struct ReduceProblem {
 };
 int launch_reduce(const ReduceProblem &p);
 // 1-D strided reduction of n elements into ONE device element (BMAS-shaped call)
+// flags: NUK_REDUCE_NO_SEED for a chunk that does not start at element 0 of the caller's array
 int reduce_1d_device(int red, int dtype, size_t n, const void *x, int64_t incx, void *out_dev,
-                     cudaStream_t stream);
+                     cudaStream_t stream, int flags = 0);
+constexpr int NUK_REDUCE_NO_SEED = 0x100;   // internal: float hmax/hmin without the x[0] rule (see k_combine_one)
 // combine `count` partial results (device, contiguous) into one device element, fixed order
 int reduce_partials_device(int red, int dtype, size_t count, const void *partials, void *out_dev,
                            cudaStream_t stream);

@@ -549,7 +549,7 @@ template <class F> int launch_map(const MapProblem &p, F f = F()) {
       d.stride[2][a] = (binary && y) ? p.sy[a] : 0;
     }
     const size_t blocks = (n + (size_t)kThreads * UNROLL - 1) / ((size_t)kThreads * UNROLL);
-    const int grid = grid_for(blocks, (int)option("grid_mult"));
+    const int grid = grid_for(blocks, (int)opt(OPT_GRID_MULT));
     k_map_nd<F, UNROLL><<<grid, kThreads, 0, p.stream>>>(n, d, x, y, out, p.xv, p.yv, f);
     return post_launch("k_map_nd");
   }

@@ -17,6 +17,7 @@
 //                   rows may be split into chunks whose partials are combined in order
 //   k_reduce_any  : anything else, one thread per output
 #include <cuda.h>   // CUtensorMap types only; the encoder is fetched with cudaGetDriverEntryPoint
+#include <atomic>
 #include <cfloat>
 #include <limits>
 #include "dispatch.cuh"
@@ -211,15 +212,27 @@ k_reduce_nd(size_t n, NdDesc d, const typename R::In *x, typename R::Acc *partia
 
 // ------------------------------------------------------------------ pass 2
 // partials laid out [count][nout]; output j combines partials[0..count)[j] in index order.
+// `first` (float extrema only): the element at index 0.  BMAS hmax / hmin fold from x[0]
+// (oracle/bmas_oracle.c DEF_HMINMAX: r = x[0]; r = (a > r) ? a : r), so a NaN survives exactly when it
+// sits in the FIRST position and is ignored anywhere else; the tree ignores every NaN, this puts the
+// first one back.
 template <class R>
 __global__ void __launch_bounds__(kThreads)
 k_combine_one(size_t count, const typename R::Acc *partials, typename R::In *o1,
-              typename R::In *o2, typename R::Acc init) {
+              typename R::In *o2, typename R::Acc init, const typename R::In *first) {
   using A = typename R::Acc;
   A acc = init;
   for (size_t i = threadIdx.x; i < count; i += kThreads) acc = R::combine(acc, partials[i]);
   acc = block_reduce<R>(acc, init);
-  if (threadIdx.x == 0) R::store(o1, o2, 0, acc);
+  if (threadIdx.x == 0) {
+    if constexpr (std::is_floating_point<typename R::In>::value && std::is_same<A, typename R::In>::value) {
+      if (first) {
+        const typename R::In f0 = *first;
+        if (f0 != f0) acc = f0;
+      }
+    }
+    R::store(o1, o2, 0, acc);
+  }
 }
 template <class R>
 __global__ void __launch_bounds__(kThreads)
@@ -609,7 +622,7 @@ template <class R> static int run_full(const ReduceProblem &p, typename R::Acc i
   void *scratch_ptr = nullptr;
   if (contig && aligned_to(x, 16)) {
     const size_t tiles = n / E / ((size_t)kThreads * UNROLL) + 1;
-    grid = grid_for(tiles, (int)option("reduce_grid_mult"));
+    grid = grid_for(tiles, (int)opt(OPT_REDUCE_GRID_MULT));
     NUK_TRY(scratch(p.stream, sizeof(A) * (size_t)grid, &scratch_ptr));
     k_reduce_flat<R, UNROLL><<<grid, kThreads, 0, p.stream>>>(n, x, static_cast<A *>(scratch_ptr), init);
     NUK_TRY(post_launch("k_reduce_flat"));
@@ -623,12 +636,14 @@ template <class R> static int run_full(const ReduceProblem &p, typename R::Acc i
       d.stride[1][a] = p.sx[a];
     }
     const size_t blocks = (n + kThreads * 4 - 1) / (kThreads * 4);
-    grid = grid_for(blocks ? blocks : 1, (int)option("reduce_grid_mult"));
+    grid = grid_for(blocks ? blocks : 1, (int)opt(OPT_REDUCE_GRID_MULT));
     NUK_TRY(scratch(p.stream, sizeof(A) * (size_t)grid, &scratch_ptr));
     k_reduce_nd<R><<<grid, kThreads, 0, p.stream>>>(n, d, x, static_cast<A *>(scratch_ptr), init);
     NUK_TRY(post_launch("k_reduce_nd"));
   }
-  k_combine_one<R><<<1, kThreads, 0, p.stream>>>((size_t)grid, static_cast<const A *>(scratch_ptr), o1, o2, init);
+  const T *first = ((p.red == NUK_HMAX || p.red == NUK_HMIN) && !(p.flags & NUK_REDUCE_NO_SEED) && n > 0) ? x : nullptr;
+  k_combine_one<R><<<1, kThreads, 0, p.stream>>>((size_t)grid, static_cast<const A *>(scratch_ptr), o1, o2, init,
+                                                 first);
   return post_launch("k_combine_one");
 }
 
@@ -709,18 +724,20 @@ template <class R> static int run_axis(const ReduceProblem &p, typename R::Acc i
                 ((ncols * (int64_t)sizeof(T)) % 16 == 0) && d.rlen >= 4 * kSeqRows && nouter <= 65535;
       for (int a = 0; a + 1 < d.orank; ++a) ok = ok && ((d.oxs[a] * (int64_t)sizeof(T)) % 16 == 0);
       const bool covers = seq_tiles * nouter * 4 >= (int64_t)dev->sm_count * 3;   // >= 75% of the SMs
-      if (ok && (covers || (p.flags & NUK_REDUCE_REF_ORDER)) && option("seq_cols") != 0) {
+      if (ok && (covers || (p.flags & NUK_REDUCE_REF_ORDER)) && opt(OPT_SEQ_COLS) != 0) {
         const size_t smem = (size_t)kSeqStages * kSeqRows * kSeqThreads * sizeof(T);
-        static bool attr_set = false;   // per template instantiation
-        if (!attr_set) {
+        // the opt-in is per (kernel instantiation, device): one bit per device ordinal
+        static std::atomic<uint64_t> attr_set{0};
+        const uint64_t dev_bit = 1ull << (dev->device & 63);
+        if (!(attr_set.load(std::memory_order_acquire) & dev_bit)) {
           NUK_CUDA(cudaFuncSetAttribute(k_reduce_cols_seq<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem));
-          attr_set = true;
+          attr_set.fetch_or(dev_bit, std::memory_order_release);
         }
         dim3 grid((unsigned)seq_tiles, (unsigned)nouter);
         // preferred: one tensor-map TMA request per stage
         EncodeTiledFn enc = encode_tiled_fn();
-        if (enc && d.orank <= 2 && d.rstride > 0 && (d.orank < 2 || d.oxs[0] > 0) && option("seq_cols") != 2) {
+        if (enc && d.orank <= 2 && d.rstride > 0 && (d.orank < 2 || d.oxs[0] > 0) && opt(OPT_SEQ_COLS) != 2) {
           CUtensorMap tmap;
           const cuuint64_t gdim[3] = {(cuuint64_t)ncols, (cuuint64_t)d.rlen, (cuuint64_t)nouter};
           const cuuint64_t outer_stride = d.orank == 2 ? (cuuint64_t)d.oxs[0] : (cuuint64_t)(d.rlen * d.rstride);
@@ -732,11 +749,11 @@ template <class R> static int run_axis(const ReduceProblem &p, typename R::Acc i
                                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
           if (r == CUDA_SUCCESS) {
-            static bool attr2_set = false;
-            if (!attr2_set) {
+            static std::atomic<uint64_t> attr2_set{0};
+            if (!(attr2_set.load(std::memory_order_acquire) & dev_bit)) {
               NUK_CUDA(cudaFuncSetAttribute(k_reduce_cols_tma<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)smem));
-              attr2_set = true;
+              attr2_set.fetch_or(dev_bit, std::memory_order_release);
             }
             k_reduce_cols_tma<R><<<grid, kSeqThreads, smem, p.stream>>>(tmap, d, ncols, o1, o2, init);
             return post_launch("k_reduce_cols_tma");
@@ -755,7 +772,7 @@ template <class R> static int run_axis(const ReduceProblem &p, typename R::Acc i
       const int64_t have = col_tiles * nouter;
       if (have < want) {
         int64_t c = (want + have - 1) / have;
-        const int64_t min_rows = option("col_split_rows") > 0 ? option("col_split_rows") : 256;
+        const int64_t min_rows = opt(OPT_COL_SPLIT_ROWS) > 0 ? opt(OPT_COL_SPLIT_ROWS) : 256;
         const int64_t maxc = (d.rlen + min_rows - 1) / min_rows;
         if (c > maxc) c = maxc;
         if (c < 1) c = 1;
@@ -854,9 +871,10 @@ int launch_reduce(const ReduceProblem &p) {
 }
 
 int reduce_1d_device(int red, int dtype, size_t n, const void *x, int64_t incx, void *out_dev,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, int flags) {
   ReduceProblem p;
   memset(&p, 0, sizeof(p));
+  p.flags = flags;
   p.red = red;
   p.dtype = dtype;
   p.rank = 1;

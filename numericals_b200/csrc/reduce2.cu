@@ -7,8 +7,17 @@
 #include <limits>
 #include "dispatch.cuh"
 #include "ops.cuh"
+#include "staging.cuh"
 
 namespace nuk {
+
+template <typename T> struct DTypeOf;
+template <> struct DTypeOf<float> { static constexpr int value = NUK_F32; };
+template <> struct DTypeOf<double> { static constexpr int value = NUK_F64; };
+template <> struct DTypeOf<int64_t> { static constexpr int value = NUK_I64; };
+template <> struct DTypeOf<int32_t> { static constexpr int value = NUK_I32; };
+template <> struct DTypeOf<int16_t> { static constexpr int value = NUK_I16; };
+template <> struct DTypeOf<int8_t> { static constexpr int value = NUK_I8; };
 
 template <typename T> struct AccT {
   using type = typename std::conditional<std::is_floating_point<T>::value, T, typename WrapT<T>::type>::type;
@@ -108,7 +117,7 @@ static int dot_device(size_t n, const T *x, int64_t ix, const T *y, int64_t iy, 
   constexpr int E = 16 / sizeof(T);
   const int vec = (ix == 1 && iy == 1 && aligned_to(x, 16) && aligned_to(y, 16)) ? 1 : 0;
   const size_t blocks = n / E / ((size_t)kThreads * 4) + 1;
-  const int grid = grid_for(blocks, (int)option("reduce_grid_mult"));
+  const int grid = grid_for(blocks, (int)opt(OPT_REDUCE_GRID_MULT));
   void *part = nullptr;
   NUK_TRY(scratch(st, sizeof(A) * (size_t)grid, &part));
   k_dot<T><<<grid, kThreads, 0, st>>>(n, x, ix, y, iy, static_cast<A *>(part), vec);
@@ -160,7 +169,7 @@ static int argred_device(size_t n, const T *x, int64_t ix, int64_t index_base, V
   else
     init = IS_MAX ? std::numeric_limits<T>::lowest() : std::numeric_limits<T>::max();
   const size_t blocks = (n + (size_t)kThreads * 4 - 1) / ((size_t)kThreads * 4);
-  const int grid = grid_for(blocks ? blocks : 1, (int)option("reduce_grid_mult"));
+  const int grid = grid_for(blocks ? blocks : 1, (int)opt(OPT_REDUCE_GRID_MULT));
   void *part = nullptr;
   NUK_TRY(scratch(st, sizeof(ValIdx<T>) * (size_t)grid, &part));
   k_argred<T, IS_MAX><<<grid, kThreads, 0, st>>>(n, x, ix, index_base, static_cast<ValIdx<T> *>(part), init);
@@ -171,81 +180,52 @@ static int argred_device(size_t n, const T *x, int64_t ix, int64_t index_base, V
 }
 
 // ------------------------------------------------------------------ value-returning wrappers
-static bool is_device_ptr(const void *p) {
-  cudaPointerAttributes a;
-  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
-    cudaGetLastError();
-    return false;
-  }
-  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
-}
-
-// stage a strided HOST chunk into a contiguous device buffer (address order); returns walk ptr/inc
-static int stage_chunk(const void *host, long inc, size_t sz, long c0, long m, void *dbuf, cudaStream_t st,
-                       const void **dp, long *di) {
-  const char *base = static_cast<const char *>(host);
-  const long ainc = inc < 0 ? -inc : inc;
-  const char *lo = inc > 0 ? base + (int64_t)c0 * inc * (int64_t)sz
-                           : base + (int64_t)(c0 + m - 1) * inc * (int64_t)sz;
-  if (ainc == 1) NUK_CUDA(cudaMemcpyAsync(dbuf, lo, (size_t)m * sz, cudaMemcpyHostToDevice, st));
-  else NUK_CUDA(cudaMemcpy2DAsync(dbuf, sz, lo, (size_t)ainc * sz, sz, (size_t)m, cudaMemcpyHostToDevice, st));
-  if (inc > 0) { *dp = dbuf; *di = 1; }
-  else { *dp = static_cast<char *>(dbuf) + (size_t)(m - 1) * sz; *di = -1; }
-  return NUK_OK;
-}
-
-struct HostStage {
-  void *bx = nullptr, *by = nullptr, *res = nullptr;
-  size_t cap = 0;
-  ~HostStage() {
-    if (bx) cudaFree(bx);
-    if (by) cudaFree(by);
-    if (res) cudaFree(res);
-  }
-  int ensure(size_t want) {
-    if (!res) NUK_CUDA(cudaMalloc(&res, 64));
-    if (cap >= want) return NUK_OK;
-    if (bx) cudaFree(bx);
-    if (by) cudaFree(by);
-    bx = by = nullptr;
-    NUK_CUDA(cudaMalloc(&bx, want));
-    NUK_CUDA(cudaMalloc(&by, want));
-    cap = want;
-    return NUK_OK;
-  }
-};
-static thread_local HostStage tl_hs;
-
+// Host operands travel through the staging ring (staging.cuh): chunk k on slot k mod S produces ONE
+// partial (a dot product / a (value, index) pair) in a per-thread device buffer; the partials are then
+// combined in chunk order by the same pass-2 kernels, so the result is a fixed function of (n, chunk size).
 template <typename T>
 static int dot_typed(long n, const void *x, long ix, const void *y, long iy, void *result) {
+  using A = typename AccT<T>::type;
   memset(result, 0, sizeof(T));
   if (n <= 0) return NUK_OK;
-  if (!device_info()) return nuk_last_status();
+  const DeviceInfo *dev = device_info();
+  if (!dev) return nuk_last_status();
   cudaStream_t st = current_stream();
-  void *pin = nullptr;
+  void *pin = nullptr, *dresv = nullptr;
   NUK_TRY(pinned_slot(&pin));
-  const bool xd = is_device_ptr(x), yd = is_device_ptr(y);
-  size_t cap = (size_t)(option("stage_mb") > 0 ? option("stage_mb") : 32) << 20;
-  NUK_TRY(tl_hs.ensure((xd && yd) ? 256 : cap));
-  T *dres = static_cast<T *>(tl_hs.res);
-  if (xd && yd) {
+  NUK_TRY(thread_buffer(BUF_RESULT, 64, &dresv));
+  T *dres = static_cast<T *>(dresv);
+  const PtrKind xk = classify_ptr(x, true), yk = classify_ptr(y, true);
+  if (xk == PK_DEVICE && yk == PK_DEVICE) {
     NUK_TRY(dot_device<T>((size_t)n, static_cast<const T *>(x), ix, static_cast<const T *>(y), iy, dres, 0, st));
   } else {
+    const size_t cap = stage_chunk_bytes((size_t)n * sizeof(T));
     const long chunk = (long)(cap / sizeof(T));
+    const long nchunks = (n + chunk - 1) / chunk;
+    Stager &sg = thread_stager();
+    NUK_TRY(sg.ensure(cap, (int)opt(OPT_STAGE_SLOTS), dev->device));
+    NUK_CUDA(cudaEventRecord(sg.entry, st));
+    for (int s = 0; s < sg.nslots; ++s) NUK_CUDA(cudaStreamWaitEvent(sg.streams[s], sg.entry, 0));
+    void *dpartv = nullptr;
+    NUK_TRY(thread_buffer(BUF_PARTS, (size_t)(nchunks + 8) * sizeof(A), &dpartv));
+    T *dpart = static_cast<T *>(dpartv);
+    const Opnd ox{x, ix, sizeof(T), xk}, oy{y, iy, sizeof(T), yk};
     long c0 = 0;
-    for (int k = 0; c0 < n; ++k, c0 += chunk) {
+    for (long k = 0; c0 < n; ++k, c0 += chunk) {
       const long m = (n - c0 < chunk) ? (n - c0) : chunk;
+      const int slot = (int)(k % sg.nslots);
+      NUK_TRY(sg.begin_slot(slot));
       const void *xp, *yp;
       long xi, yi;
-      if (xd) { xp = static_cast<const char *>(x) + (int64_t)c0 * ix * (int64_t)sizeof(T); xi = ix; }
-      else if (ix == 0) { NUK_CUDA(cudaMemcpyAsync(tl_hs.bx, x, sizeof(T), cudaMemcpyHostToDevice, st)); xp = tl_hs.bx; xi = 0; }
-      else NUK_TRY(stage_chunk(x, ix, sizeof(T), c0, m, tl_hs.bx, st, &xp, &xi));
-      if (yd) { yp = static_cast<const char *>(y) + (int64_t)c0 * iy * (int64_t)sizeof(T); yi = iy; }
-      else if (iy == 0) { NUK_CUDA(cudaMemcpyAsync(tl_hs.by, y, sizeof(T), cudaMemcpyHostToDevice, st)); yp = tl_hs.by; yi = 0; }
-      else NUK_TRY(stage_chunk(y, iy, sizeof(T), c0, m, tl_hs.by, st, &yp, &yi));
-      NUK_TRY(dot_device<T>((size_t)m, static_cast<const T *>(xp), xi, static_cast<const T *>(yp), yi, dres,
-                            k > 0, st));
+      if (xk == PK_DEVICE) { xp = static_cast<const char *>(x) + (int64_t)c0 * ix * (int64_t)sizeof(T); xi = ix; }
+      else NUK_TRY(sg.in(slot, 0, ox, c0, m, &xp, &xi));
+      if (yk == PK_DEVICE) { yp = static_cast<const char *>(y) + (int64_t)c0 * iy * (int64_t)sizeof(T); yi = iy; }
+      else NUK_TRY(sg.in(slot, 1, oy, c0, m, &yp, &yi));
+      NUK_TRY(dot_device<T>((size_t)m, static_cast<const T *>(xp), xi, static_cast<const T *>(yp), yi, dpart + k, 0,
+                            sg.streams[slot]));
     }
+    NUK_TRY(sg.finish_all());
+    NUK_TRY(reduce_partials_device(NUK_SUM, DTypeOf<T>::value, (size_t)nchunks, dpart, dres, st));
   }
   NUK_CUDA(cudaMemcpyAsync(pin, dres, sizeof(T), cudaMemcpyDeviceToHost, st));
   NUK_CUDA(cudaStreamSynchronize(st));
@@ -256,28 +236,45 @@ static int dot_typed(long n, const void *x, long ix, const void *y, long iy, voi
 template <typename T, bool IS_MAX>
 static int argred_typed(long n, const void *x, long ix, long *result) {
   *result = 0;
-  if (n <= 0) return NUK_OK;
-  if (!device_info()) return nuk_last_status();
+  if (n <= 0 || ix == 0) return NUK_OK;
+  const DeviceInfo *dev = device_info();
+  if (!dev) return nuk_last_status();
   cudaStream_t st = current_stream();
-  void *pin = nullptr;
+  void *pin = nullptr, *dresv = nullptr;
   NUK_TRY(pinned_slot(&pin));
-  const bool xd = is_device_ptr(x);
-  size_t cap = (size_t)(option("stage_mb") > 0 ? option("stage_mb") : 32) << 20;
-  NUK_TRY(tl_hs.ensure(xd ? 256 : cap));
-  ValIdx<T> *dres = static_cast<ValIdx<T> *>(tl_hs.res);
-  if (xd) {
+  NUK_TRY(thread_buffer(BUF_RESULT, 64, &dresv));
+  ValIdx<T> *dres = static_cast<ValIdx<T> *>(dresv);
+  const PtrKind xk = classify_ptr(x, true);
+  if (xk == PK_DEVICE) {
     NUK_TRY((argred_device<T, IS_MAX>((size_t)n, static_cast<const T *>(x), ix, 0, dres, 0, st)));
   } else {
+    const size_t cap = stage_chunk_bytes((size_t)n * sizeof(T));
     const long chunk = (long)(cap / sizeof(T));
+    const long nchunks = (n + chunk - 1) / chunk;
+    Stager &sg = thread_stager();
+    NUK_TRY(sg.ensure(cap, (int)opt(OPT_STAGE_SLOTS), dev->device));
+    void *dpartv = nullptr;
+    NUK_TRY(thread_buffer(BUF_PARTS, (size_t)(nchunks + 8) * sizeof(ValIdx<T>), &dpartv));
+    ValIdx<T> *dpart = static_cast<ValIdx<T> *>(dpartv);
+    const Opnd ox{x, ix, sizeof(T), xk};
     long c0 = 0;
-    for (int k = 0; c0 < n; ++k, c0 += chunk) {
+    for (long k = 0; c0 < n; ++k, c0 += chunk) {
       const long m = (n - c0 < chunk) ? (n - c0) : chunk;
+      const int slot = (int)(k % sg.nslots);
+      NUK_TRY(sg.begin_slot(slot));
       const void *xp;
       long xi;
-      if (ix == 0) { *result = 0; return NUK_OK; }
-      NUK_TRY(stage_chunk(x, ix, sizeof(T), c0, m, tl_hs.bx, st, &xp, &xi));
-      NUK_TRY((argred_device<T, IS_MAX>((size_t)m, static_cast<const T *>(xp), xi, c0, dres, k > 0, st)));
+      NUK_TRY(sg.in(slot, 0, ox, c0, m, &xp, &xi));
+      NUK_TRY((argred_device<T, IS_MAX>((size_t)m, static_cast<const T *>(xp), xi, c0, dpart + k, 0, sg.streams[slot])));
     }
+    NUK_TRY(sg.finish_all());
+    T init;
+    if (std::is_floating_point<T>::value)
+      init = IS_MAX ? -std::numeric_limits<T>::infinity() : std::numeric_limits<T>::infinity();
+    else
+      init = IS_MAX ? std::numeric_limits<T>::lowest() : std::numeric_limits<T>::max();
+    k_argred_combine<T, IS_MAX><<<1, kThreads, 0, st>>>((size_t)nchunks, dpart, dres, 0, init);
+    NUK_TRY(post_launch("k_argred_combine"));
   }
   NUK_CUDA(cudaMemcpyAsync(pin, dres, sizeof(ValIdx<T>), cudaMemcpyDeviceToHost, st));
   NUK_CUDA(cudaStreamSynchronize(st));

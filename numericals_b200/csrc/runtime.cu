@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -83,6 +84,16 @@ const DeviceInfo *device_info() {
 cudaStream_t current_stream() { return tl_stream; }
 void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// NUK_LOG=1: one stderr line per kernel launch (kernel family, device, thread) -- the env-gated
+// per-call log of SURVEY section 5; read once.
+static int log_level() {
+  static const int lv = [] {
+    const char *v = getenv("NUK_LOG");
+    return v ? atoi(v) : 0;
+  }();
+  return lv;
+}
+
 int post_launch(const char *kernel) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -90,35 +101,60 @@ int post_launch(const char *kernel) {
     return NUK_ERR_CUDA;
   }
   count_launch();
+  if (log_level() > 0)
+    fprintf(stderr, "[libnuk] launch %-20s dev %d launch# %llu\n", kernel, tl_device,
+            (unsigned long long)g_launches.load(std::memory_order_relaxed));
   return NUK_OK;
 }
 
 // ------------------------------------------------------------------ knobs
-static std::unordered_map<std::string, long> &options() {
-  static std::unordered_map<std::string, long> o = [] {
-    std::unordered_map<std::string, long> m;
-    m["grid_mult"] = 8;        // resident CTAs per SM targeted by persistent map kernels
-    m["reduce_grid_mult"] = 16; // CTAs per SM in pass 1 of full reductions (16: sum/max f32/f64 +7 % over 8, profiles/reduce_grid_r01.txt)
-    m["stage_mb"] = 32;        // chunk size of the host-pointer staging pipeline
-    m["stage_slots"] = 3;
-    m["col_split_rows"] = 256; // rows per CTA in the split column reduction
-    m["seq_cols"] = 1;         // 1: TMA-fed sequential (reference-order) column reduction where it fits
-    const char *names[] = {"grid_mult", "reduce_grid_mult", "stage_mb", "stage_slots", "col_split_rows",
-                           "seq_cols"};
-    for (const char *n : names) {
-      std::string env = "NUK_";
-      for (const char *c = n; *c; ++c) env.push_back((char)toupper(*c));
-      if (const char *v = getenv(env.c_str())) m[n] = atol(v);
-    }
-    return m;
-  }();
-  return o;
+// Plain atomics indexed by Opt: the launch path reads them without a lock or a string hash (the
+// reference calls the C layer from concurrent lparallel workers, src/transcendental/lparallel.lisp:70-96).
+static const char *const kOptNames[OPT_COUNT] = {"grid_mult", "reduce_grid_mult", "stage_mb", "stage_slots",
+                                                 "col_split_rows", "seq_cols", "stage_threads", "rows_ctas_per_sm"};
+static std::atomic<long> g_opts[OPT_COUNT];
+static std::once_flag g_opts_once;
+static void init_opts() {
+  g_opts[OPT_GRID_MULT] = 8;          // resident CTAs per SM targeted by the persistent nd map kernel
+  g_opts[OPT_REDUCE_GRID_MULT] = 16;  // CTAs per SM in pass 1 of full reductions (profiles/reduce_grid_r01.txt)
+  g_opts[OPT_STAGE_MB] = 32;          // chunk size of the host-pointer staging pipeline
+  g_opts[OPT_STAGE_SLOTS] = 3;
+  g_opts[OPT_COL_SPLIT_ROWS] = 256;   // rows per CTA in the split column reduction
+  g_opts[OPT_SEQ_COLS] = 1;           // 1: TMA-fed sequential (reference-order) column reduction where it fits
+  g_opts[OPT_STAGE_THREADS] = 0;      // host mover threads for pageable / strided host operands (0 = auto)
+  g_opts[OPT_ROWS_CTAS_PER_SM] = 0;   // rows kernel: CTAs per SM the row grouping aims for (0 = built-in rule)
+  for (int i = 0; i < OPT_COUNT; ++i) {
+    std::string env = "NUK_";
+    for (const char *c = kOptNames[i]; *c; ++c) env.push_back((char)toupper(*c));
+    if (const char *v = getenv(env.c_str())) g_opts[i] = atol(v);
+  }
 }
-long option(const char *name) {
-  std::lock_guard<std::mutex> lk(g_mu);
-  auto &o = options();
-  auto it = o.find(name);
-  return it == o.end() ? -1 : it->second;
+long opt(Opt o) {
+  std::call_once(g_opts_once, init_opts);
+  return g_opts[o].load(std::memory_order_relaxed);
+}
+static int opt_index(const char *name) {
+  for (int i = 0; i < OPT_COUNT; ++i)
+    if (name && !strcmp(name, kOptNames[i])) return i;
+  return -1;
+}
+
+// ------------------------------------------------------------------ pointer classification
+static thread_local int tl_ptr_mode = NUK_PTR_AUTO;
+PtrKind classify_ptr(const void *p, bool strided) {
+  if (!p) return PK_NULL;
+  if (strided && tl_ptr_mode == NUK_PTR_DEVICE) return PK_DEVICE;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return PK_PAGEABLE;
+  }
+  switch (a.type) {
+    case cudaMemoryTypeDevice:
+    case cudaMemoryTypeManaged: return PK_DEVICE;
+    case cudaMemoryTypeHost: return PK_HOST;
+    default: return PK_PAGEABLE;
+  }
 }
 
 int grid_for(size_t work_blocks, int blocks_per_sm) {
@@ -129,24 +165,42 @@ int grid_for(size_t work_blocks, int blocks_per_sm) {
 }
 
 // ------------------------------------------------------------------ scratch arenas
+// Everything a thread caches on a device is keyed by the DEVICE it was allocated on: a thread that
+// moves between devices with nuk_init (the single-process multi-GPU mode does, once per call) must
+// never hand a kernel a pointer into another device's memory.
 struct Arena {
   void *ptr = nullptr;
   size_t bytes = 0;
 };
+struct ArenaKey {
+  int device;
+  cudaStream_t stream;
+  bool operator==(const ArenaKey &o) const { return device == o.device && stream == o.stream; }
+};
+struct ArenaKeyHash {
+  size_t operator()(const ArenaKey &k) const {
+    return std::hash<const void *>()(k.stream) * 31u + (size_t)(k.device + 1);
+  }
+};
 struct ThreadState {
-  std::unordered_map<cudaStream_t, Arena> arenas;
+  std::unordered_map<ArenaKey, Arena, ArenaKeyHash> arenas;
+  std::vector<Arena> bufs;   // [device * BUF_COUNT + slot]
   void *pinned = nullptr;
   ~ThreadState() {
     // contexts may already be gone at thread exit; ignore errors
     for (auto &kv : arenas)
       if (kv.second.ptr) cudaFree(kv.second.ptr);
+    for (auto &b : bufs)
+      if (b.ptr) cudaFree(b.ptr);
     if (pinned) cudaFreeHost(pinned);
   }
 };
 static thread_local ThreadState tl_state;
 
 int scratch(cudaStream_t s, size_t bytes, void **dptr) {
-  Arena &a = tl_state.arenas[s];
+  const DeviceInfo *d = device_info();
+  if (!d) return nuk_last_status();
+  Arena &a = tl_state.arenas[ArenaKey{d->device, s}];
   if (a.bytes < bytes) {
     if (a.ptr) {
       NUK_CUDA(cudaStreamSynchronize(s));  // earlier kernels may still read the old arena
@@ -162,8 +216,39 @@ int scratch(cudaStream_t s, size_t bytes, void **dptr) {
   return NUK_OK;
 }
 
+static void drop_arena(cudaStream_t s) {   // nuk_stream_destroy: a recycled handle must not inherit the arena
+  for (auto it = tl_state.arenas.begin(); it != tl_state.arenas.end();) {
+    if (it->first.stream == s) {
+      if (it->second.ptr) cudaFree(it->second.ptr);
+      it = tl_state.arenas.erase(it);
+    } else {
+      ++it;
+    }
+  }
+}
+
+int thread_buffer(BufSlot slot, size_t bytes, void **dptr) {
+  const DeviceInfo *d = device_info();
+  if (!d) return nuk_last_status();
+  const size_t idx = (size_t)d->device * BUF_COUNT + (size_t)slot;
+  if (tl_state.bufs.size() <= idx) tl_state.bufs.resize(idx + 1);
+  Arena &a = tl_state.bufs[idx];
+  if (a.bytes < bytes) {
+    if (a.ptr) {
+      NUK_CUDA(cudaDeviceSynchronize());
+      NUK_CUDA(cudaFree(a.ptr));
+      a.ptr = nullptr;
+      a.bytes = 0;
+    }
+    NUK_CUDA(cudaMalloc(&a.ptr, bytes < 256 ? 256 : bytes));
+    a.bytes = bytes < 256 ? 256 : bytes;
+  }
+  *dptr = a.ptr;
+  return NUK_OK;
+}
+
 int pinned_slot(void **hptr) {
-  if (!tl_state.pinned) NUK_CUDA(cudaHostAlloc(&tl_state.pinned, 512, cudaHostAllocDefault));
+  if (!tl_state.pinned) NUK_CUDA(cudaHostAlloc(&tl_state.pinned, 512, cudaHostAllocPortable));
   *hptr = tl_state.pinned;
   return NUK_OK;
 }
@@ -239,6 +324,7 @@ NUK_API int nuk_stream_create(nuk_stream_t *s) {
   return NUK_OK;
 }
 NUK_API int nuk_stream_destroy(nuk_stream_t s) {
+  drop_arena((cudaStream_t)s);
   NUK_CUDA(cudaStreamDestroy((cudaStream_t)s));
   return NUK_OK;
 }
@@ -339,19 +425,62 @@ NUK_API int nuk_pointer_is_device(const void *p) {
   }
   return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? 1 : 0;
 }
-
-NUK_API int nuk_set_option(const char *name, long value) {
-  std::lock_guard<std::mutex> lk(g_mu);
-  auto &o = options();
-  auto it = o.find(name);
-  if (it == o.end()) {
-    set_error(NUK_ERR_INVALID, "unknown option %s", name);
+NUK_API int nuk_set_pointer_mode(int mode) {
+  if (mode != NUK_PTR_AUTO && mode != NUK_PTR_DEVICE) {
+    set_error(NUK_ERR_INVALID, "unknown pointer mode %d", mode);
     return NUK_ERR_INVALID;
   }
-  it->second = value;
+  tl_ptr_mode = mode;
   return NUK_OK;
 }
-NUK_API long nuk_get_option(const char *name) { return option(name); }
+NUK_API int nuk_get_pointer_mode(void) { return tl_ptr_mode; }
+
+// ------------------------------------------------------------------ CUDA graphs
+// A launch-bound inner loop (C1: 10^6-element maps, 3-4 us of GPU work per call) is captured once and
+// replayed: every map / axis-reduction entry point is capture-safe (no allocation, no sync) once its
+// scratch arena exists, i.e. after one ordinary warm-up call on the same stream.
+NUK_API int nuk_graph_begin(nuk_stream_t s) {
+  if (!device_info()) return nuk_last_status();
+  if (!s) {
+    set_error(NUK_ERR_INVALID, "graph capture needs a stream created with nuk_stream_create");
+    return NUK_ERR_INVALID;
+  }
+  NUK_CUDA(cudaStreamBeginCapture((cudaStream_t)s, cudaStreamCaptureModeRelaxed));
+  return NUK_OK;
+}
+NUK_API int nuk_graph_end(nuk_stream_t s, nuk_graph_t *g) {
+  cudaGraph_t graph = nullptr;
+  NUK_CUDA(cudaStreamEndCapture((cudaStream_t)s, &graph));
+  cudaGraphExec_t exec = nullptr;
+  cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGraphInstantiate", __FILE__, __LINE__);
+  *g = exec;
+  return NUK_OK;
+}
+NUK_API int nuk_graph_launch(nuk_graph_t g, nuk_stream_t s) {
+  NUK_CUDA(cudaGraphLaunch((cudaGraphExec_t)g, (cudaStream_t)s));
+  return NUK_OK;
+}
+NUK_API int nuk_graph_destroy(nuk_graph_t g) {
+  if (g) NUK_CUDA(cudaGraphExecDestroy((cudaGraphExec_t)g));
+  return NUK_OK;
+}
+
+NUK_API int nuk_set_option(const char *name, long value) {
+  const int i = opt_index(name);
+  if (i < 0) {
+    set_error(NUK_ERR_INVALID, "unknown option %s", name ? name : "(null)");
+    return NUK_ERR_INVALID;
+  }
+  opt((Opt)i);   // make sure the defaults / environment were applied first
+  g_opts[i].store(value, std::memory_order_relaxed);
+  return NUK_OK;
+}
+NUK_API long nuk_get_option(const char *name) {
+  const int i = opt_index(name);
+  return i < 0 ? -1 : opt((Opt)i);
+}
 NUK_API unsigned long long nuk_launch_count(void) { return g_launches.load(); }
 
 // L2 flush: overwrite a buffer of 2x the L2 size (benchmark hygiene only)

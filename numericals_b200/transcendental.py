@@ -67,10 +67,17 @@ def log(x, base=None, out=None, broadcast=None):
     here (NUK_LOGB: 12 bytes per element, the same bits -- an IEEE division of the two rounded logs)."""
     if base is None:
         return _log1(x, out=out, broadcast=broadcast)
-    if _is_number(base) or _is_number(x):
+    import math
+    if _is_number(x) and _is_number(base):
+        return math.log(x) / math.log(base)
+    if _is_number(base):
+        # (nu:log array number): log of the array, then a divide by the host-side scalar log
         lx = _log1(x, out=out, broadcast=broadcast)
-        lb = _log1(base) if not _is_number(base) else __import__("math").log(base)
-        return divide(lx, lb, out=lx, broadcast=True)
+        return divide(lx, math.log(base), out=lx, broadcast=True)
+    if _is_number(x):
+        # (nu:log number array): the scalar's log is taken on the host; OUT has BASE's shape
+        lb = _log1(base, out=out, broadcast=broadcast)
+        return divide(math.log(x), lb, out=lb, broadcast=True)
     return _two_arg_float("log-base", x, base, out, broadcast)
 
 
