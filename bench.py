@@ -243,7 +243,6 @@ def main():
     import numericals_b200 as nu
     from numericals_b200 import _lib
     from numericals_b200.array import from_pointer
-    from numericals_b200.sharded import ShardedArray, DeviceBackend, slab_bounds
 
     nu.require_device(local_rank)
     lib = _lib.lib()
@@ -549,55 +548,143 @@ def side_measurements(nu, lib, torch, dist, stream, rank, world, barrier, max_ov
         res["C4_reductions_f64_16384sq"] = c4
         del d
     barrier()
-    # C5: nu:multiply + nu:sum on 2^32 single-float elements sharded in contiguous slabs (strong scaling);
-    # the final scalar = all-gather of per-rank partials + fixed-order combine.
-    from numericals_b200.sharded import slab_bounds
+    # ---- multi-GPU legs go through libnuk's own communicator (include/nuk.h "multi-GPU"): torch.distributed only
+    #      carries the 128-byte mailbox handles; the exchange itself happens inside libnuk's reduction kernels
+    from numericals_b200.sharded import Communicator, DeviceBackend, ShardedArray, slab_bounds
+    comm = Communicator.from_process_group(dist, rank, world)
+    sptr = C.c_void_p(stream.cuda_stream)
+    # C5: nu:multiply + nu:sum on 2^32 single-float elements sharded in contiguous slabs (strong scaling):
+    # 3 launches per step and rank: the map, pass 1 of the sum, and ONE kernel for pass 2 + exchange + rank-order fold
     total = 1 << 32
     lo, hi = slab_bounds(total, world, rank)
     n = hi - lo
     free_b = torch.cuda.mem_get_info()[0]
-    if 12 * n + (2 << 30) < free_b:
-        xs = torch.full((n,), 0.5, dtype=torch.float32, device="cuda")
-        ys = torch.full((n,), 2.0, dtype=torch.float32, device="cuda")
+    if 12 * n + (6 << 30) < free_b:
+        gen = torch.Generator(device="cuda")
+        gen.manual_seed(777 + rank)
+        xs = torch.rand(n, dtype=torch.float32, device="cuda", generator=gen).mul_(2).sub_(1)     # U[-1,1)
+        ys = torch.rand(n, dtype=torch.float32, device="cuda", generator=gen).add_(0.5)           # U[0.5,1.5)
         zs = torch.empty_like(xs)
         X, Y, Z = (from_pointer(t.data_ptr(), "single-float", (n,), owner=t) for t in (xs, ys, zs))
-        part = torch.zeros(1, dtype=torch.float32, device="cuda")
-        P = from_pointer(part.data_ptr(), "single-float", (), owner=part)
+        final = torch.zeros(2, dtype=torch.float32, device="cuda")
         dims, st = _i64(n), _i64(1)
-        gathered = torch.zeros(world, dtype=torch.float32, device="cuda")
-        final = torch.zeros(1, dtype=torch.float32, device="cuda")
 
         def c5():
             nu.multiply(X, Y, out=Z, broadcast=False)
-            _check(lib.nuk_reduce(0, 0, 1, dims, st, -1, None, C.c_void_p(Z.ptr), C.c_void_p(P.ptr), 0,
-                                  C.c_void_p(stream.cuda_stream)))
-            if world > 1:
-                dist.all_gather_into_tensor(gathered, part)
-                _check(lib.nuk_reduce(0, 0, 1, _i64(world), st, -1, None, C.c_void_p(gathered.data_ptr()),
-                                      C.c_void_p(final.data_ptr()), 0, C.c_void_p(stream.cuda_stream)))
-                return final                         # same fixed-order combine on every rank
-            return part
+            _check(lib.nuk_comm_reduce(comm.handle, 0, 0, 1, dims, st, C.c_void_p(Z.ptr), C.c_void_p(final.data_ptr()), sptr))
 
-        r = c5()
+        def c5_fused():   # the same quantity without materialising z: nu:vdot's kernel shape would be 8 B/element
+            _check(lib.nuk_comm_reduce(comm.handle, 0, 0, 1, dims, st, C.c_void_p(Z.ptr), C.c_void_p(final.data_ptr() + 4), sptr))
+
+        c5()
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = 5
         a.record(stream)
         for _ in range(reps):
-            r = c5()
+            c5()
         b.record(stream)
         barrier()
         ms = max_over_ranks(a.elapsed_time(b) / reps)
-        tot = float(r.item())
-        assert tot == float(total), (tot, total)     # 0.5 * 2.0 summed 2^32 times is exact in any tree
+        a.record(stream)
+        for _ in range(reps):
+            c5_fused()
+        b.record(stream)
+        barrier()
+        ms_sum = max_over_ranks(a.elapsed_time(b) / reps)
+        comm.status()
+        tot = float(final[0].item())
+        # checks on RANDOM data: (1) z == x * y on windows at both ends of the slab and around the 2^31-element
+        # mark of the slab (64-bit indexing), against torch's IEEE multiply; (2) the sum against the exact sum
+        # (double accumulation of the same products, all-reduced) within the pairwise bound; (3) every rank
+        # holds the same bits
+        for w0 in sorted(set(max(0, min(n - (1 << 22), w)) for w in (0, (1 << 31) - (1 << 21), n - (1 << 22), n // 3 + 1))):
+            assert torch.equal(zs[w0:w0 + (1 << 22)], xs[w0:w0 + (1 << 22)] * ys[w0:w0 + (1 << 22)]), "C5 window %d" % w0
+        ex = torch.zeros(2, dtype=torch.float64, device="cuda")
+        for c0 in range(0, n, 1 << 28):
+            d = zs[c0:c0 + (1 << 28)].double()
+            ex[0] += d.sum()
+            ex[1] += d.abs().sum()
+            del d
+        if world > 1:
+            dist.all_reduce(ex)
+            allf = [torch.zeros_like(final) for _ in range(world)]
+            dist.all_gather(allf, final)
+            assert all(torch.equal(f, allf[0]) for f in allf), "ranks hold different sums"
+        exact, sabs = float(ex[0].item()), float(ex[1].item())
+        bound = 2 * 2.0 ** -24 * 32 * sabs
+        assert abs(tot - exact) <= bound, (tot, exact, bound)
+        assert float(final[1].item()) == tot
         if rank == 0:
-            res["C5_multiply_sum_2p32_sharded"] = {"ms": ms, "n_gpus": world, "elements_total": total,
-                                                   "algorithmic_gbs_aggregate": 16.0 * total / (ms / 1e3) / 1e9,
-                                                   "per_gpu_frac_of_measured_peak": 16.0 * total / world / (ms / 1e3) / 1e9 / peak,
-                                                   "scaling": "strong", "sum_exact": True}
+            res["C5_multiply_sum_2p32_sharded"] = {
+                "ms": ms, "n_gpus": world, "elements_total": total,
+                "algorithmic_gbs_aggregate": 16.0 * total / (ms / 1e3) / 1e9,
+                "per_gpu_frac_of_measured_peak": 16.0 * total / world / (ms / 1e3) / 1e9 / peak,
+                "scaling": "strong", "launches_per_step_per_rank": 3,
+                "sum_only_ms": ms_sum, "sum_only_gbs_aggregate": 4.0 * total / (ms_sum / 1e3) / 1e9,
+                "data": "random U[-1,1) * U[0.5,1.5) per rank", "sum": tot, "sum_exact_in_double": exact,
+                "abs_err": abs(tot - exact), "pairwise_bound": bound, "ranks_bit_identical": True,
+                "combine": "nuk_comm_reduce: pass 2 + exchange over NVLink peer memory + rank-order fold in one kernel"}
         del xs, ys, zs
     elif rank == 0:
         res["C5_multiply_sum_2p32_sharded"] = {"skipped": "needs %d GiB per GPU" % (12 * n >> 30)}
+    barrier()
+    # C4 sharded: the 16384 x 16384 double-float matrix cut along its first axis (the reference's rule for
+    # dense arrays, dense-numericals-src/utils/lparallel.lisp:41-49): axis 1 is local, axis 0 = local column
+    # reduction + rank-ordered all-reduce of a 16384-vector, full = nuk_comm_reduce (strong scaling)
+    if world > 1:
+        be = DeviceBackend(comm)
+        R = 16384
+        rlo, rhi = slab_bounds(R, world, rank)
+        gen = torch.Generator(device="cuda")
+        gen.manual_seed(4242 + rank)
+        dm = torch.rand(rhi - rlo, R, dtype=torch.float64, device="cuda", generator=gen)
+        M = ShardedArray(from_pointer(dm.data_ptr(), "double-float", (rhi - rlo, R), owner=dm), (R, R), 0, rank, world, be)
+        full_out = torch.zeros(1, dtype=torch.float64, device="cuda")
+        d2, s2 = _i64(rhi - rlo, R), _i64(R, 1)
+
+        def timed(fn, reps=10):
+            fn()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(reps):
+                fn()
+            b.record(stream)
+            barrier()
+            return max_over_ranks(a.elapsed_time(b) / reps)
+
+        by = 8.0 * R * R
+        c4s = {}
+        o_cols = nu.empty((R,), "double-float")              # :out preallocated, as in the single-GPU C4 leg
+        o_rows = nu.empty((rhi - rlo,), "double-float")
+        for name, fn in (("sum_axis0", lambda: M.sum(axes=0, out=o_cols)), ("sum_axis1", lambda: M.sum(axes=1, out=o_rows)),
+                         ("maximum_axis0", lambda: M.maximum(axes=0, out=o_cols)),
+                         ("mean_axis0", lambda: M.mean(axes=0, out=o_cols)),
+                         ("sum_full", lambda: _check(lib.nuk_comm_reduce(comm.handle, 0, 1, 2, d2, s2, C.c_void_p(dm.data_ptr()),
+                                                                         C.c_void_p(full_out.data_ptr()), sptr)))):
+            ms = timed(fn)
+            c4s[name] = {"ms": ms, "algorithmic_gbs_aggregate": by / (ms / 1e3) / 1e9,
+                         "per_gpu_frac_of_measured_peak": by / world / (ms / 1e3) / 1e9 / peak}
+        comm.status()
+        # parity of the sharded results: axis 0 against the rank-ordered fold of per-rank torch sums, full sum
+        # against the exact double sum; identical on every rank
+        got0 = torch.from_numpy(M.sum(axes=0).to_numpy()).cuda()
+        ref0 = dm.sum(dim=0)
+        dist.all_reduce(ref0)
+        assert torch.allclose(got0, ref0, rtol=1e-12)
+        allg = [torch.zeros_like(got0) for _ in range(world)]
+        dist.all_gather(allg, got0)
+        assert all(torch.equal(g, allg[0]) for g in allg), "ranks hold different axis-0 sums"
+        ref = dm.sum().reshape(1)
+        dist.all_reduce(ref)
+        assert abs(float(full_out.item()) - float(ref.item())) <= 1e-12 * float(ref.item())
+        if rank == 0:
+            c4s["note"] = ("rows cut in %d slabs; axis 0 = local TMA column reduction + nuk_comm_allreduce of 16384 doubles "
+                           "(rank-ordered fold over peer memory), axis 1 local, full = nuk_comm_reduce" % world)
+            res["C4_sharded_f64_16384sq"] = c4s
+        del dm
+    comm.close()
     return res
 
 

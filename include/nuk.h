@@ -47,7 +47,8 @@ enum {
   NUK_ERR_CUDA = 2,        /* CUDA runtime error (message holds cudaGetErrorString) */
   NUK_ERR_UNSUPPORTED = 3, /* (op, dtype) has no translation, like the reference's
                               "No CFUNCTION known for ..." (src/utils/translations.lisp:37) */
-  NUK_ERR_NO_DEVICE = 4
+  NUK_ERR_NO_DEVICE = 4,
+  NUK_ERR_COMM = 5         /* multi-GPU: no peer access, or a peer never arrived at a collective */
 };
 const char *nuk_last_error(void);
 int nuk_last_status(void);
@@ -226,6 +227,51 @@ int nuk_moments(int dtype, int rank, const int64_t *dims, const int64_t *sx, int
  * (src/statistics/variance.lisp:58-68): S=S*S; S=S/cnt; Q=Q-S; Q=Q/(cnt-ddof). Result in q. */
 int nuk_variance_finish(int dtype, int64_t n, void *s_sum, void *q_sumsq, double count,
                         double ddof, nuk_stream_t s);
+
+/* ------------------------------------------------------------------ multi-GPU (one box, <= 8 GPUs)
+ * The path shards by contiguous slabs -- the reference's own thread-slicing rule lifted to devices:
+ * ceiling(n / workers) units per worker, the last one takes what is left
+ * (src/transcendental/lparallel.lisp:60-96), and for an nd array the FIRST axis that is long enough is the
+ * one that is cut (dense-numericals-src/utils/lparallel.lisp:41-49).  Elementwise maps and reductions that
+ * keep the cut axis are purely local (call the ordinary entry points on the slab).  What needs an exchange is
+ * the combine step of a reduction over the cut axis; the last kernel of the reduction does it itself over
+ * NVLink peer memory and folds the per-rank values IN RANK ORDER, so all ranks hold bit-identical results and
+ * the result is reproducible for a given world size.
+ *
+ * One process, all GPUs (a Common Lisp image):  nuk_comm_init_all(n, NULL, comms); then per collective one
+ * call PER communicator, all issued before any of them is waited for (they are asynchronous on the stream
+ * given; each communicator's call switches to its device and back).
+ * One process per GPU:  nuk_comm_create on the rank's device, nuk_comm_export -> exchange the
+ * NUK_COMM_HANDLE_BYTES-byte handles with whatever the host has (rank order) -> nuk_comm_connect.
+ * Every rank must issue the same sequence of collectives.  A peer that does not arrive within
+ * NUK_COMM_TIMEOUT_MS (environment, default 20000) makes the kernels give up; nuk_comm_status and every
+ * later collective then return NUK_ERR_COMM. */
+typedef struct nuk_comm *nuk_comm_t;
+#define NUK_COMM_HANDLE_BYTES 128
+int nuk_shard_bounds(int64_t n, int world, int rank, int64_t *lo, int64_t *hi);
+int nuk_shard_axis(int rank, const int64_t *dims, int world);   /* the axis to cut, -1 if none is long enough */
+int nuk_comm_init_all(int ndev, const int *devices /* NULL = 0..ndev-1 */, nuk_comm_t *comms);
+int nuk_comm_create(int world, int rank, nuk_comm_t *comm);      /* on the calling thread's device */
+int nuk_comm_export(nuk_comm_t comm, void *handle_out);
+int nuk_comm_connect(nuk_comm_t comm, const void *all_handles);  /* world * NUK_COMM_HANDLE_BYTES, rank order */
+int nuk_comm_destroy(nuk_comm_t comm);
+int nuk_comm_world(nuk_comm_t comm);
+int nuk_comm_rank(nuk_comm_t comm);
+int nuk_comm_device(nuk_comm_t comm);
+int nuk_comm_status(nuk_comm_t comm);
+/* out[i] = local_0[i] (+) local_1[i] (+) ... (+) local_{W-1}[i] for i < count, (+) = sum / max / min of `red`;
+ * local and out are device arrays of this rank (out may be local).  The combine of an axis reduction over the
+ * cut axis: nuk_reduce on the slab into `local`, then this. */
+int nuk_comm_allreduce(nuk_comm_t comm, int red, int dtype, int64_t count, const void *local, void *out,
+                       nuk_stream_t s);
+/* FULL reduction of the whole sharded array: x describes this rank's slab (dims / element strides as in
+ * nuk_reduce); out receives the global result on every rank (one device element).  Two launches: pass 1 over
+ * the slab, then pass 2 + exchange + rank-order fold in one kernel. */
+int nuk_comm_reduce(nuk_comm_t comm, int red, int dtype, int rank, const int64_t *dims, const int64_t *sx,
+                    const void *x, void *out, nuk_stream_t s);
+/* global sum(x) and sum(x*x) in one pass over the slab (nu:variance / nu:std on a sharded array) */
+int nuk_comm_moments(nuk_comm_t comm, int dtype, int rank, const int64_t *dims, const int64_t *sx,
+                     const void *x, void *sum_out, void *sumsq_out, nuk_stream_t s);
 
 /* ------------------------------------------------------------------ resolver
  * The "utils broadcast/stride resolver": numpy right-aligned rule of

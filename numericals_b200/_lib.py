@@ -13,6 +13,7 @@ LIB_PATH = os.environ.get("NUK_LIB") or os.path.join(_HERE, "lib", "libnuk.so") 
 
 NUK_MAX_RANK = 8
 NUK_OK = 0
+COMM_HANDLE_BYTES = 128    # NUK_COMM_HANDLE_BYTES
 
 # dtype codes = column of the reference translation table (src/utils/translations.lisp:66-82)
 F32, F64, I64, I32, I16, I8, U64, U32, U16, U8 = 0, 1, 3, 4, 5, 6, 7, 8, 9, 10
@@ -103,6 +104,14 @@ def _declare(L):
                                   C.POINTER(C.c_int), _i64p, _i64p],
         "nuk_coalesce": [C.c_int, C.c_int, _i64p, _i64p],
         "nuk_selftest_seeds": [C.c_uint32, C.c_uint32, C.POINTER(C.c_ulonglong), _vp],
+        "nuk_shard_bounds": [C.c_int64, C.c_int, C.c_int, _i64p, _i64p], "nuk_shard_axis": [C.c_int, _i64p, C.c_int],
+        "nuk_comm_init_all": [C.c_int, C.POINTER(C.c_int), C.POINTER(_vp)],
+        "nuk_comm_create": [C.c_int, C.c_int, C.POINTER(_vp)], "nuk_comm_export": [_vp, _vp],
+        "nuk_comm_connect": [_vp, _vp], "nuk_comm_destroy": [_vp], "nuk_comm_world": [_vp], "nuk_comm_rank": [_vp],
+        "nuk_comm_device": [_vp], "nuk_comm_status": [_vp],
+        "nuk_comm_allreduce": [_vp, C.c_int, C.c_int, C.c_int64, _vp, _vp, _vp],
+        "nuk_comm_reduce": [_vp, C.c_int, C.c_int, C.c_int, _i64p, _i64p, _vp, _vp, _vp],
+        "nuk_comm_moments": [_vp, C.c_int, C.c_int, _i64p, _i64p, _vp, _vp, _vp, _vp],
     }.items():
         fn = getattr(L, name)
         fn.argtypes = args

@@ -34,6 +34,7 @@ struct DeviceInfo {
   size_t l2_bytes;
 };
 const DeviceInfo *device_info();      // current device of this thread (lazy init); nullptr + error if none
+int use_device(int dev);              // make `dev` the calling thread's device (CUDA's and libnuk's notion)
 cudaStream_t current_stream();        // thread-local stream used by BMAS_* symbols
 void count_launch(unsigned n = 1);    // gpu_launches bookkeeping
 int post_launch(const char *kernel);  // cudaGetLastError -> status (+ the NUK_LOG per-launch line)
@@ -41,7 +42,7 @@ int post_launch(const char *kernel);  // cudaGetLastError -> status (+ the NUK_L
 // NUK_* knobs: lock-free reads on the launch path (nuk_set_option / the environment write them)
 enum Opt {
   OPT_GRID_MULT = 0, OPT_REDUCE_GRID_MULT, OPT_STAGE_MB, OPT_STAGE_SLOTS, OPT_COL_SPLIT_ROWS, OPT_SEQ_COLS,
-  OPT_STAGE_THREADS, OPT_ROWS_CTAS_PER_SM, OPT_COUNT
+  OPT_STAGE_THREADS, OPT_ROWS_CTAS_PER_SM, OPT_STAGE_BOUNCE, OPT_COUNT
 };
 long opt(Opt o);
 

@@ -37,6 +37,11 @@ struct ReduceProblem {
   void *out2;                      // second output for fused moments (sum of squares), or null
   int flags;
   cudaStream_t stream;
+  // sharded FULL reduction (comm.cu): pass 2 is fused with the rank-ordered exchange over peer memory,
+  // pass-1 partials live in the communicator's own buffer (no allocation inside a collective)
+  const struct CommLink *link;
+  void *link_partials;
+  size_t link_partial_bytes;
 };
 int launch_reduce(const ReduceProblem &p);
 // 1-D strided reduction of n elements into ONE device element (BMAS-shaped call)

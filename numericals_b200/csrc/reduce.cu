@@ -22,6 +22,7 @@
 #include <limits>
 #include "dispatch.cuh"
 #include "ops.cuh"
+#include "comm.cuh"
 
 namespace nuk {
 
@@ -247,6 +248,20 @@ k_combine_cols(int64_t count, int64_t nout, const typename R::Acc *partials, typ
   for (int64_t k = 0; k < count; ++k) acc = R::combine(acc, partials[k * nout + j]);
   const int64_t a = j / ncols, c = j - a * ncols;
   R::store(o1, o2, a * ostride_outer + c * ostride_col, acc);
+}
+
+// ------------------------------------------------------------------ multi-GPU combine (comm.cuh)
+template <class R>
+__global__ void __launch_bounds__(kThreads)
+k_combine_allgather(CommLink link, size_t count, const typename R::Acc *partials, typename R::In *o1,
+                    typename R::In *o2, typename R::Acc init, const typename R::In *first) {
+  combine_allgather_body<R>(link, count, partials, o1, o2, init, first,
+                            [](typename R::Acc v, typename R::Acc i) { return block_reduce<R>(v, i); });
+}
+template <class R>
+__global__ void __launch_bounds__(kThreads)
+k_allreduce(CommLink link, int64_t count, const typename R::In *local, typename R::In *out) {
+  allreduce_body<R>(link, count, local, out);
 }
 
 // ------------------------------------------------------------------ axis reductions
@@ -620,10 +635,21 @@ template <class R> static int run_full(const ReduceProblem &p, typename R::Acc i
   constexpr int E = 16 / sizeof(T);
   int grid;
   void *scratch_ptr = nullptr;
+  // pass-1 partials: the thread's arena, or the communicator's own buffer for a sharded reduction
+  auto partial_space = [&](size_t bytes, void **ptr) -> int {
+    if (!p.link) return scratch(p.stream, bytes, ptr);
+    if (bytes > p.link_partial_bytes) {
+      set_error(NUK_ERR_INVALID, "internal: communicator partial buffer too small (%zu > %zu)", bytes,
+                p.link_partial_bytes);
+      return NUK_ERR_INVALID;
+    }
+    *ptr = p.link_partials;
+    return NUK_OK;
+  };
   if (contig && aligned_to(x, 16)) {
     const size_t tiles = n / E / ((size_t)kThreads * UNROLL) + 1;
     grid = grid_for(tiles, (int)opt(OPT_REDUCE_GRID_MULT));
-    NUK_TRY(scratch(p.stream, sizeof(A) * (size_t)grid, &scratch_ptr));
+    NUK_TRY(partial_space(sizeof(A) * (size_t)grid, &scratch_ptr));
     k_reduce_flat<R, UNROLL><<<grid, kThreads, 0, p.stream>>>(n, x, static_cast<A *>(scratch_ptr), init);
     NUK_TRY(post_launch("k_reduce_flat"));
   } else {
@@ -637,11 +663,16 @@ template <class R> static int run_full(const ReduceProblem &p, typename R::Acc i
     }
     const size_t blocks = (n + kThreads * 4 - 1) / (kThreads * 4);
     grid = grid_for(blocks ? blocks : 1, (int)opt(OPT_REDUCE_GRID_MULT));
-    NUK_TRY(scratch(p.stream, sizeof(A) * (size_t)grid, &scratch_ptr));
+    NUK_TRY(partial_space(sizeof(A) * (size_t)grid, &scratch_ptr));
     k_reduce_nd<R><<<grid, kThreads, 0, p.stream>>>(n, d, x, static_cast<A *>(scratch_ptr), init);
     NUK_TRY(post_launch("k_reduce_nd"));
   }
   const T *first = ((p.red == NUK_HMAX || p.red == NUK_HMIN) && !(p.flags & NUK_REDUCE_NO_SEED) && n > 0) ? x : nullptr;
+  if (p.link) {
+    k_combine_allgather<R><<<1, kThreads, 0, p.stream>>>(*p.link, (size_t)grid, static_cast<const A *>(scratch_ptr), o1,
+                                                         o2, init, first);
+    return post_launch("k_combine_allgather");
+  }
   k_combine_one<R><<<1, kThreads, 0, p.stream>>>((size_t)grid, static_cast<const A *>(scratch_ptr), o1, o2, init,
                                                  first);
   return post_launch("k_combine_one");
@@ -867,6 +898,52 @@ int launch_reduce(const ReduceProblem &p) {
     case NUK_U8: return by_red<uint8_t>(p);
   }
   set_error(NUK_ERR_UNSUPPORTED, "no reduction kernel for dtype %d", p.dtype);
+  return NUK_ERR_UNSUPPORTED;
+}
+
+// rank-ordered all-reduce of `count` elements (one mailbox slot at most; comm.cu loops over larger payloads)
+template <typename T> static int allreduce_typed(const CommLink &link, int red, int64_t count, const void *local,
+                                                 void *out, cudaStream_t stream) {
+  // enough CTAs to keep the NVLink stores in flight, never more than the flag table holds; a function of
+  // `count` only, so every rank launches the same grid
+  int64_t g = (count * (int64_t)sizeof(T) + 8191) / 8192;
+  if (g < 1) g = 1;
+  if (g > kCommMaxCtas) g = kCommMaxCtas;
+  const T *l = static_cast<const T *>(local);
+  T *o = static_cast<T *>(out);
+  switch (red) {
+    case NUK_SUM:
+    case NUK_SUMSQ: k_allreduce<SumR<T>><<<(unsigned)g, kThreads, 0, stream>>>(link, count, l, o); break;
+    case NUK_HMAX: k_allreduce<MaxR<T>><<<(unsigned)g, kThreads, 0, stream>>>(link, count, l, o); break;
+    case NUK_HMIN: k_allreduce<MinR<T>><<<(unsigned)g, kThreads, 0, stream>>>(link, count, l, o); break;
+    default:
+      set_error(NUK_ERR_UNSUPPORTED, "all-reduce: unknown reduction %d", red);
+      return NUK_ERR_UNSUPPORTED;
+  }
+  return post_launch("k_allreduce");
+}
+int launch_allreduce(const CommLink &link, int red, int dtype, int64_t count, const void *local, void *out,
+                     cudaStream_t stream) {
+  int dt = dtype;
+  if (red == NUK_SUM || red == NUK_SUMSQ) {   // unsigned sums through the signed symbol: same bits
+    if (dt == NUK_U64) dt = NUK_I64;
+    if (dt == NUK_U32) dt = NUK_I32;
+    if (dt == NUK_U16) dt = NUK_I16;
+    if (dt == NUK_U8) dt = NUK_I8;
+  }
+  switch (dt) {
+    case NUK_F32: return allreduce_typed<float>(link, red, count, local, out, stream);
+    case NUK_F64: return allreduce_typed<double>(link, red, count, local, out, stream);
+    case NUK_I64: return allreduce_typed<int64_t>(link, red, count, local, out, stream);
+    case NUK_I32: return allreduce_typed<int32_t>(link, red, count, local, out, stream);
+    case NUK_I16: return allreduce_typed<int16_t>(link, red, count, local, out, stream);
+    case NUK_I8: return allreduce_typed<int8_t>(link, red, count, local, out, stream);
+    case NUK_U64: return allreduce_typed<uint64_t>(link, red, count, local, out, stream);
+    case NUK_U32: return allreduce_typed<uint32_t>(link, red, count, local, out, stream);
+    case NUK_U16: return allreduce_typed<uint16_t>(link, red, count, local, out, stream);
+    case NUK_U8: return allreduce_typed<uint8_t>(link, red, count, local, out, stream);
+  }
+  set_error(NUK_ERR_UNSUPPORTED, "all-reduce: no kernel for dtype %d", dtype);
   return NUK_ERR_UNSUPPORTED;
 }
 

@@ -71,6 +71,14 @@ static int select_device(int dev) {
   return NUK_OK;
 }
 
+int use_device(int dev) {
+  if (dev == tl_device) {
+    int cur = -1;
+    if (cudaGetDevice(&cur) == cudaSuccess && cur == dev) return NUK_OK;
+  }
+  return select_device(dev);
+}
+
 const DeviceInfo *device_info() {
   if (tl_device < 0) {
     int dev = 0;
@@ -111,7 +119,8 @@ int post_launch(const char *kernel) {
 // Plain atomics indexed by Opt: the launch path reads them without a lock or a string hash (the
 // reference calls the C layer from concurrent lparallel workers, src/transcendental/lparallel.lisp:70-96).
 static const char *const kOptNames[OPT_COUNT] = {"grid_mult", "reduce_grid_mult", "stage_mb", "stage_slots",
-                                                 "col_split_rows", "seq_cols", "stage_threads", "rows_ctas_per_sm"};
+                                                 "col_split_rows", "seq_cols", "stage_threads", "rows_ctas_per_sm",
+                                                 "stage_bounce"};
 static std::atomic<long> g_opts[OPT_COUNT];
 static std::once_flag g_opts_once;
 static void init_opts() {
@@ -122,6 +131,7 @@ static void init_opts() {
   g_opts[OPT_COL_SPLIT_ROWS] = 256;   // rows per CTA in the split column reduction
   g_opts[OPT_SEQ_COLS] = 1;           // 1: TMA-fed sequential (reference-order) column reduction where it fits
   g_opts[OPT_STAGE_THREADS] = 0;      // host mover threads for pageable / strided host operands (0 = auto)
+  g_opts[OPT_STAGE_BOUNCE] = 1;       // 0: hand pageable |inc| == 1 operands to the driver's own pageable copy (A/B only)
   g_opts[OPT_ROWS_CTAS_PER_SM] = 0;   // rows kernel: CTAs per SM the row grouping aims for (0 = built-in rule)
   for (int i = 0; i < OPT_COUNT; ++i) {
     std::string env = "NUK_";

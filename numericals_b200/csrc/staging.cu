@@ -211,7 +211,7 @@ int Stager::in(int slot, int which, const Opnd &o, long c0, long m, const void *
   void *dbuf = buf[slot][which];
   const size_t bytes = (size_t)m * o.size;
   const bool unit = (o.inc == 1 || o.inc == -1);
-  if (unit && o.kind == PK_HOST) {             // direct
+  if (unit && (o.kind == PK_HOST || opt(OPT_STAGE_BOUNCE) == 0)) {             // direct
     NUK_CUDA(cudaMemcpyAsync(dbuf, chunk_lo(o, c0, m), bytes, cudaMemcpyHostToDevice, st));
   } else {
     void *bb = nullptr;
@@ -246,7 +246,7 @@ int Stager::out(int slot, const Opnd &o, long c0, long m) {
   cudaStream_t st = streams[slot];
   const size_t bytes = (size_t)m * o.size;
   const bool unit = (o.inc == 1 || o.inc == -1);
-  if (unit && o.kind == PK_HOST) {
+  if (unit && (o.kind == PK_HOST || opt(OPT_STAGE_BOUNCE) == 0)) {
     NUK_CUDA(cudaMemcpyAsync(const_cast<char *>(chunk_lo(o, c0, m)), buf[slot][2], bytes, cudaMemcpyDeviceToHost, st));
     return NUK_OK;
   }

@@ -84,11 +84,11 @@ def test_c3_broadcast_shapes_bit_exact(nu, refnu):
     v = rng.random(4096, dtype=np.float32)
     out = nu.empty((4096, 4096), "single-float")
     nu.multiply(nu.asarray(m), nu.asarray(v), out=out)
-    assert out.to_numpy().tobytes() == refnu.two_arg("multiply", m, v).tobytes()
+    assert out.to_numpy().tobytes() == refnu.two_arg("mul", m, v).tobytes()
     # in place on the matrix operand (nu:multiply! a v): OUT aliases X at full size
     dm = nu.asarray(m)
     nu.multiply(dm, nu.asarray(v), out=dm)
-    assert dm.to_numpy().tobytes() == refnu.two_arg("multiply", m, v).tobytes()
+    assert dm.to_numpy().tobytes() == refnu.two_arg("mul", m, v).tobytes()
 
 
 # ------------------------------------------------------------------------------------------------ C4
