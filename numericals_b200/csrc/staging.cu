@@ -45,9 +45,12 @@ Pool *pool() {
     Pool *pp = new Pool;
     long want = opt(OPT_STAGE_THREADS);
     if (want <= 0) {
+      // all cores but the caller's, at most 15: the copies are bandwidth-bound and 15 movers were 1.26x faster
+      // than 8 on a 16-vCPU box (profiles/time_pageable_r02_a.txt); the reference's own lparallel kernel
+      // also takes every core (src/transcendental/lparallel.lisp:60-64)
       const unsigned hc = std::thread::hardware_concurrency();
-      want = hc >= 4 ? (long)(hc / 2) : 1;
-      if (want > 8) want = 8;
+      want = hc >= 2 ? (long)(hc - 1) : 1;
+      if (want > 15) want = 15;
     }
     if (want > 64) want = 64;
     pp->nthreads = (int)want;
@@ -144,9 +147,10 @@ static void scatter(const void *src, const Opnd &o, long c0, long m) {
     }
   });
 }
+void copy_stream(void *dst, const void *src, size_t n);   // hostcopy.cpp: non-temporal stores
 static void par_memcpy(void *dst, const void *src, size_t bytes) {
   host_parallel_for(bytes, (size_t)1 << 20, [&](size_t lo, size_t hi) {
-    memcpy(static_cast<char *>(dst) + lo, static_cast<const char *>(src) + lo, hi - lo);
+    copy_stream(static_cast<char *>(dst) + lo, static_cast<const char *>(src) + lo, hi - lo);
   });
 }
 

@@ -53,7 +53,17 @@ namespace nuk {
     NUK_D float operator()(float a, float b) const { return nukmath::FN(a, b); } \
   };
 // sin / cos capped at 32 registers (cos 92 -> 97 %, profiles/minblocks_sweep_r01.txt)
-NUK_F32_UNARY_FAST(SinF, sin_f32, 4, 8, NUK_FAST_TRIG32) NUK_F32_UNARY_FAST(CosF, cos_f32, 4, 8, NUK_FAST_TRIG32) NUK_F32_UNARY(TanhF, tanh_f32)
+#ifndef NUK_FAST_TANH32
+#define NUK_FAST_TANH32 false
+#endif
+#ifndef NUK_TANH32_MINB
+#define NUK_TANH32_MINB 0
+#endif
+#ifndef NUK_TRIG32_MINB
+#define NUK_TRIG32_MINB 8
+#endif
+NUK_F32_UNARY_FAST(SinF, sin_f32, 4, NUK_TRIG32_MINB, NUK_FAST_TRIG32) NUK_F32_UNARY_FAST(CosF, cos_f32, 4, NUK_TRIG32_MINB, NUK_FAST_TRIG32)
+NUK_F32_UNARY_FAST(TanhF, tanh_f32, 4, NUK_TANH32_MINB, NUK_FAST_TANH32)
 NUK_F32_UNARY(LogF, log_f32)
 NUK_F32_UNARY_U(ExpF, exp_f32, 2)   // 5.9 TB/s with 2 packs per thread vs 5.2 with 4 (profiles/membench_r01.txt)
 NUK_F32_UNARY_FAST(TanF, tan_f32, NUK_F32_UNROLL, 0, NUK_FAST_TRIG32) NUK_F32_VIA_F64(AsinF, asin_f32) NUK_F32_VIA_F64(AcosF, acos_f32)

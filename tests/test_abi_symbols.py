@@ -68,3 +68,28 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")) or f == "Makefile":
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "import oracle" not in text and "from oracle" not in text and "liboracle" not in text, f
+
+
+def test_lisp_stub_binds_exported_symbols_and_defines_what_it_exports():
+    """lisp/nuk-cffi.lisp cannot be executed here (no Lisp in the image); at least every C name it binds
+    must be exported by libnuk.so and every symbol its package exports must have a definition."""
+    from numericals_b200 import _lib
+    lib = _lib.lib()
+    text = open(os.path.join(ROOT, "lisp", "nuk-cffi.lisp")).read()
+    cnames = re.findall(r'\(cffi:defcfun \("(\w+)"', text)
+    assert len(cnames) >= 40
+    missing = [n for n in cnames if not hasattr(lib, n)]
+    assert not missing, missing
+    export = re.search(r"\(:export(.*?)\)\)\s*\(in-package", text, re.S).group(1)
+    exported = set(re.findall(r"#:([^\s()]+)", export))
+    defined = set(re.findall(r"\((?:defun|defmacro|defconstant|defvar|define-condition)\s+([^\s()]+)", text))
+    defined |= set(re.findall(r'\(cffi:defcfun \("\w+"\s+([^\s()]+)\)', text))
+    for name in re.findall(r"\(defstruct \(([^\s()]+)", text):
+        defined |= {name, "make-" + name, name + "-pointer"}
+    undefined = sorted(exported - defined)
+    assert not undefined, undefined
+    # the enum values the stub hard-codes are the header's
+    hdr = subprocess.check_output(["gcc", "-E", "-P", os.path.join(ROOT, "include", "nuk.h")]).decode()
+    for lisp, c in (("+logb+ 13", "NUK_LOGB"), ("+not+ 21", "NUK_NOT"), ("+sumsq+ 3", "NUK_SUMSQ"), ("+u8+ 10", "NUK_U8")):
+        assert ("(defconstant " + lisp + ")") in text, lisp
+    assert "NUK_LOGB" in hdr and "NUK_PTR_DEVICE = 1" in hdr
