@@ -239,6 +239,115 @@ k_map_flat(size_t n, const typename F::In *x, const typename F::In *y, typename 
   }
 }
 
+// ------------------------------------------------------------------ flat kernel, broadcast operands
+// OUT is one contiguous block of nrows x ncols elements (the usual case: :out preallocated, or a fresh
+// result); each input is either laid out like OUT (kind 0), a ROW vector repeated down the rows (kind 1:
+// index = column), a COLUMN vector repeated along the rows (kind 2: index = row * stride) or a scalar
+// (kind 3).  Same one-tile-per-CTA streaming structure as k_map_flat -- the tile walks OUT's flat index and
+// the broadcast operands are addressed by (row, column) recovered with ONE division per thread (ncols >=
+// kThreads * E, so consecutive packs of a thread wrap at most one row).  This is the C3 shape of
+// BASELINE.json: (4096 x 4096) * (4096) moved at 0.62 of the HBM peak through the row-looping k_map_rows
+// (a 64-bit division chain per CTA, loads of row r+1 stuck behind the stores of row r) while the flat
+// kernel moves the same bytes at 0.88 - 1.03 (profiles/time_c3_r02.txt).
+template <class F, int UNROLL>
+__global__ void __launch_bounds__(kThreads, MapMinBlocks<F>::value)
+k_map_flat2(size_t n, int64_t ncols, const typename F::In *x, const typename F::In *y, typename F::Out *out,
+            int xk, int yk, int64_t xrs, int64_t yrs, Scalar64 xv, Scalar64 yv, F f) {
+  using In = typename F::In;
+  using Out = typename F::Out;
+  using P = PackOf<F>;
+  constexpr int E = P::E;
+  using PIn = typename P::PIn;
+  using POut = typename P::POut;
+  const size_t npack = n / E;                      // ncols % E == 0, so n % E == 0: no element tail
+  constexpr size_t kTile = (size_t)kThreads * UNROLL;
+  const size_t nfull = npack / kTile;
+  POut *op = reinterpret_cast<POut *>(out);
+  const In xs = scalar_as<In>(xv), ys = scalar_as<In>(yv);
+
+  auto load = [&](const In *ptr, int kind, int64_t rs, In sv, size_t pk, int64_t r, int64_t c) -> PIn {
+    PIn v;
+    if (kind == 0) return ld_stream(reinterpret_cast<const PIn *>(ptr) + pk);
+    if (kind == 1) return ld_keep(reinterpret_cast<const PIn *>(ptr + c));
+    const In s = (kind == 2) ? ptr[r * rs] : sv;
+#pragma unroll
+    for (int e = 0; e < E; ++e) v.v[e] = s;
+    return v;
+  };
+  auto compute = [&](const PIn &a, const PIn &b) -> POut {
+    POut r;
+    if constexpr (Word4<F>::ok) {
+      uint32_t wa[4], wb[4], wr[4];
+      memcpy(wa, &a, 16);
+      memcpy(wb, &b, 16);
+#pragma unroll
+      for (int w = 0; w < 4; ++w) wr[w] = Word4<F>::op(wa[w], wb[w]);
+      memcpy(&r, wr, 16);
+    } else if constexpr (HasFast<F>::value) {
+      bool slow[E], any = false;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        slow[e] = false;
+        r.v[e] = apply_fast(f, a.v[e], F::kArity == 2 ? b.v[e] : In(), slow[e]);
+        any |= slow[e];
+      }
+      if (any) {
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+          if (slow[e]) r.v[e] = apply(f, a.v[e], F::kArity == 2 ? b.v[e] : In());
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < E; ++e) r.v[e] = apply(f, a.v[e], F::kArity == 2 ? b.v[e] : In());
+    }
+    return r;
+  };
+
+  // A column-vector operand is ONE dependent load per pack from a vector nobody else keeps warm: with HBM busy
+  // absorbing the write stream a cold line took microseconds to arrive and every CTA that needed it stalled
+  // ((8192 x 1) + (1 x 8192): 54 us cold vs 42 us with the vector in L2, profiles/time_c3_r02.txt).  Each CTA
+  // therefore asks L2 for the line it will NOT need for another ~2048 CTAs (and the first CTAs for the head).
+  if (threadIdx.x == 0 && (xk == 2 || (F::kArity == 2 && yk == 2))) {
+    const int64_t nrows = (int64_t)(n / (size_t)ncols);
+    const int64_t ahead = (int64_t)((2048 * kTile * E) / (size_t)ncols) + 32;
+    const int64_t r0 = (int64_t)(((size_t)blockIdx.x * kTile * E) / (size_t)ncols);
+    const int64_t want[2] = {r0 + ahead, (int64_t)blockIdx.x};
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (want[k] < nrows && (k == 0 || want[k] < ahead)) {
+        if (xk == 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(x + want[k] * xrs));
+        if (F::kArity == 2 && yk == 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(y + want[k] * yrs));
+      }
+    }
+  }
+  if (blockIdx.x < nfull) {
+    const size_t base = (size_t)blockIdx.x * kTile + threadIdx.x;
+    int64_t r = (int64_t)((base * E) / (size_t)ncols);
+    int64_t c = (int64_t)(base * E) - r * ncols;
+    PIn a[UNROLL], b[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      a[u] = load(x, xk, xrs, xs, base + (size_t)u * kThreads, r, c);
+      if (F::kArity == 2) b[u] = load(y, yk, yrs, ys, base + (size_t)u * kThreads, r, c);
+      c += (int64_t)kThreads * E;
+      if (c >= ncols) { c -= ncols; ++r; }
+    }
+    stage_tables(f);
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) st_stream(op + base + (size_t)u * kThreads, compute(a[u], b[u]));
+  } else {
+    stage_tables(f);
+    for (size_t pk = nfull * kTile + threadIdx.x; pk < npack; pk += kThreads) {
+      const int64_t r = (int64_t)((pk * E) / (size_t)ncols);
+      const int64_t c = (int64_t)(pk * E) - r * ncols;
+      const PIn a = load(x, xk, xrs, xs, pk, r, c);
+      PIn b = a;
+      if (F::kArity == 2) b = load(y, yk, yrs, ys, pk, r, c);
+      st_stream(op + pk, compute(a, b));
+    }
+  }
+}
+
 // ------------------------------------------------------------------ rows kernel
 struct RowsDesc {
   int64_t ncols;                 // inner (contiguous) extent
@@ -484,6 +593,31 @@ template <class F> int launch_map(const MapProblem &p, F f = F()) {
       return post_launch("k_map_flat");
     }
   }
+  // ---- flat with broadcast operands: rank 2, OUT one contiguous block, inputs laid out like OUT / row vector /
+  //      column vector / scalar (k_map_flat2)
+  if (p.rank == 2 && p.so[1] == 1 && p.so[0] == p.dims[1] && p.dims[1] >= (int64_t)kThreads * E && p.dims[1] % E == 0 &&
+      aligned_to(out, sizeof(typename P::POut)) && opt(OPT_ROWS_RPC) == 0) {
+    const int64_t ncols = p.dims[1];
+    auto kind_of = [&](const In *ptr, int64_t s0, int64_t s1) -> int {
+      if (ptr == nullptr || (s0 == 0 && s1 == 0)) return 3;
+      if (s1 == 1 && s0 == ncols) return aligned_to(ptr, sizeof(typename P::PIn)) ? 0 : -1;
+      if (s1 == 1 && s0 == 0) return aligned_to(ptr, sizeof(typename P::PIn)) ? 1 : -1;
+      if (s1 == 0) return 2;
+      return -1;
+    };
+    const int xk = kind_of(x, p.sx[0], p.sx[1]);
+    const int yk = binary ? kind_of(y, p.sy[0], p.sy[1]) : 3;
+    constexpr int FU = MapUnroll<F>::value;
+    const size_t nfull = n / E / ((size_t)kThreads * FU);
+    if (xk >= 0 && yk >= 0 && nfull + 1 <= 0x7fffffffu) {
+      Scalar64 xv = p.xv, yv = p.yv;
+      // a (0, 0)-strided operand that lives in device memory is a one-element array: kind 2 with stride 0
+      const int xk2 = (xk == 3 && x != nullptr) ? 2 : xk, yk2 = (yk == 3 && binary && y != nullptr) ? 2 : yk;
+      k_map_flat2<F, FU><<<(unsigned)(nfull + 1), kThreads, 0, p.stream>>>(
+          n, ncols, x, y, out, xk2, yk2, xk2 == 2 ? p.sx[0] : 0, yk2 == 2 ? p.sy[0] : 0, xv, yv, f);
+      return post_launch("k_map_flat2");
+    }
+  }
   // ---- rows: rank >= 2, inner axis contiguous for out, inputs 1/0 along it
   if (p.rank >= 2 && p.so[last] == 1 && (x == nullptr || p.sx[last] == 1 || p.sx[last] == 0) &&
       (!binary || y == nullptr || p.sy[last] == 1 || p.sy[last] == 0) && p.dims[last] >= 64) {
@@ -542,6 +676,7 @@ template <class F> int launch_map(const MapProblem &p, F f = F()) {
         rpc = (tiles + k * cap - 1) / (k * cap);
         if (rpc <= 32) break;
       }
+      if (opt(OPT_ROWS_RPC) > 0) rpc = opt(OPT_ROWS_RPC);
       if (rpc > d.nrows) rpc = d.nrows;
       d.rows_per_cta = (int)rpc;
       const int64_t row_groups = (d.nrows + rpc - 1) / rpc;

@@ -13,6 +13,9 @@
 
 namespace nuk {
 
+int reduce_1d_device(int red, int dtype, size_t n, const void *x, int64_t incx, void *out_dev, cudaStream_t stream,
+                     int flags);   // reduce.cu
+
 // ------------------------------------------------------------------ errors
 static thread_local int tl_status = NUK_OK;
 static thread_local char tl_msg[512] = "";
@@ -120,7 +123,7 @@ int post_launch(const char *kernel) {
 // reference calls the C layer from concurrent lparallel workers, src/transcendental/lparallel.lisp:70-96).
 static const char *const kOptNames[OPT_COUNT] = {"grid_mult", "reduce_grid_mult", "stage_mb", "stage_slots",
                                                  "col_split_rows", "seq_cols", "stage_threads", "rows_ctas_per_sm",
-                                                 "stage_bounce"};
+                                                 "stage_bounce", "rows_rpc"};
 static std::atomic<long> g_opts[OPT_COUNT];
 static std::once_flag g_opts_once;
 static void init_opts() {
@@ -132,6 +135,7 @@ static void init_opts() {
   g_opts[OPT_SEQ_COLS] = 1;           // 1: TMA-fed sequential (reference-order) column reduction where it fits
   g_opts[OPT_STAGE_THREADS] = 0;      // host mover threads for pageable / strided host operands (0 = auto)
   g_opts[OPT_STAGE_BOUNCE] = 1;       // 0: hand pageable |inc| == 1 operands to the driver's own pageable copy (A/B only)
+  g_opts[OPT_ROWS_RPC] = 0;           // rows kernel: rows per CTA (0 = built-in rule)
   g_opts[OPT_ROWS_CTAS_PER_SM] = 0;   // rows kernel: CTAs per SM the row grouping aims for (0 = built-in rule)
   for (int i = 0; i < OPT_COUNT; ++i) {
     std::string env = "NUK_";
@@ -493,7 +497,10 @@ NUK_API long nuk_get_option(const char *name) {
 }
 NUK_API unsigned long long nuk_launch_count(void) { return g_launches.load(); }
 
-// L2 flush: overwrite a buffer of 2x the L2 size (benchmark hygiene only)
+// L2 flush (benchmark hygiene only): overwrite a buffer of 2x the L2 size, then READ it back.  The write alone
+// leaves ~126 MB of DIRTY lines whose write-back is charged to whatever kernel runs next (a 128 MiB map then
+// competes with as much eviction traffic as it moves itself: C3b at 4096^2 measured 0.59 of the HBM peak for
+// that reason); after the read pass the cache holds clean lines only, which are dropped for free.
 NUK_API int nuk_flush_l2(nuk_stream_t s) {
   const DeviceInfo *d = device_info();
   if (!d) return nuk_last_status();
@@ -505,7 +512,7 @@ NUK_API int nuk_flush_l2(nuk_stream_t s) {
     std::lock_guard<std::mutex> lk(mu);
     auto it = bufs.find(d->device);
     if (it == bufs.end()) {
-      NUK_CUDA(cudaMalloc(&buf, bytes));
+      NUK_CUDA(cudaMalloc(&buf, bytes + 256));
       bufs[d->device] = buf;
     } else {
       buf = it->second;
@@ -513,7 +520,7 @@ NUK_API int nuk_flush_l2(nuk_stream_t s) {
   }
   static thread_local int flip = 0;
   NUK_CUDA(cudaMemsetAsync(buf, (flip++) & 0xff, bytes, (cudaStream_t)s));
-  return NUK_OK;
+  return reduce_1d_device(NUK_SUM, NUK_I32, bytes / 4, buf, 1, static_cast<char *>(buf) + bytes, (cudaStream_t)s, 0);
 }
 
 // ------------------------------------------------------------------ resolver

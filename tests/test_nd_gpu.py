@@ -219,3 +219,52 @@ def test_expt_atan2_ladder(nu, refnu):
                 assert ulp_distance(got.reshape(-1), want.reshape(-1)).max() <= 1, (api, dt, shape)
     x = nu.asarray(rnd(rng, np.float32, 100, 1, 10))
     assert np.allclose(nu.log(x, 2.0).to_numpy(), np.log2(x.to_numpy()), rtol=3e-7)
+
+
+@pytest.mark.parametrize("prefix,ncols", [("s", 1024), ("s", 4100), ("d", 512), ("d", 2050), ("i16", 2048), ("u8", 4096), ("i64", 1000)])
+def test_contiguous_out_with_broadcast_operands_flat2(prefix, ncols, nu, libnuk, refnu):
+    """k_map_flat2 (OUT one contiguous block; operands laid out like OUT, row vector, column vector or scalar --
+    the BASELINE C3 shapes): every operand-kind pair, full tiles + the ragged last tile, in-place, compare and
+    cast outputs; bit-exact against the oracle's per-row calls, and identical to the row-looping kernel."""
+    rng = np.random.default_rng(31)
+    dt = NP_OF[prefix]
+    et = ETYPE_OF[prefix]
+    is_f = prefix in ("s", "d")
+    nrows = 37
+    full = rnd(rng, dt, (nrows, ncols))
+    kinds = {"full": full, "row": rnd(rng, dt, (1, ncols)), "vec": rnd(rng, dt, (ncols,)), "col": rnd(rng, dt, (nrows, 1)),
+             "one": rnd(rng, dt, (1, 1))}
+    dev = {k: nu.asarray(v, type=et) for k, v in kinds.items()}
+    for kx in kinds:
+        for ky in kinds:
+            if kx != "full" and ky != "full" and not ({kx, ky} & {"row", "vec"} and {kx, ky} & {"col"}):
+                continue                                           # the result must be (nrows, ncols)
+            for api, op in (("multiply", "mul"), ("two_arg_max", "max")) + ((("divide", "div"),) if is_f else ()):
+                out = nu.empty((nrows, ncols), et)
+                getattr(nu, api)(dev[kx], dev[ky], out=out)
+                want = refnu.two_arg(op, kinds[kx], kinds[ky])
+                assert same(out.to_numpy(), want), (prefix, ncols, kx, ky, api)
+                libnuk.nuk_set_option(b"rows_rpc", 3)              # the same call through k_map_rows
+                try:
+                    out2 = nu.empty((nrows, ncols), et)
+                    getattr(nu, api)(dev[kx], dev[ky], out=out2)
+                finally:
+                    libnuk.nuk_set_option(b"rows_rpc", 0)
+                assert same(out2.to_numpy(), want), (prefix, ncols, kx, ky, api, "rows kernel")
+            c = nu.two_arg_lt(dev[kx], dev[ky])
+            assert same(c.to_numpy(), refnu.compare("lt", kinds[kx], kinds[ky])), (prefix, ncols, kx, ky)
+    # scalar polymorphs (host scalar by value) and in-place on the full operand
+    s = kinds["one"][0, 0].item()
+    assert same(nu.multiply(dev["full"], s).to_numpy(), refnu.two_arg("mul", full, np.full((1,), s, dtype=dt)))
+    z = nu.asarray(full, type=et)
+    nu.multiply(z, dev["vec"], out=z)
+    assert same(z.to_numpy(), refnu.two_arg("mul", full, kinds["vec"]))
+    if not is_f:
+        assert same(nu.astype(dev["full"], "double-float").to_numpy(), full.astype(np.float64))
+    else:
+        nu.sqrt(nu.abs(dev["full"]), out=z)
+        assert same(z.to_numpy(), np.sqrt(np.abs(full)))
+    # 3-D that coalesces to the same problem: (3, 7, ncols) * (ncols)
+    t3 = rnd(rng, dt, (3, 7, ncols))
+    got = nu.multiply(nu.asarray(t3, type=et), dev["vec"]).to_numpy()
+    assert same(got, refnu.two_arg("mul", t3, kinds["vec"]))
