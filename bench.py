@@ -199,6 +199,34 @@ def run_reference(args, emit):
 
 
 # ------------------------------------------------------------------------------ GPU arm
+def bind_near_gpu(torch, local_rank, world):
+    """Host threads of this rank (and libnuk's mover threads, which inherit the mask) onto the cores that are
+    local to the rank's GPU: the e2e legs stream 8 GiB per step through host memory, and on a two-socket box a
+    page-locked buffer that lands on the other socket halves the link.  No-op when the platform exposes a
+    single NUMA node (numa_node = -1) or when there is only one rank."""
+    info = {"numa_node": None, "cpus": None}
+    try:
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0" % (dom, bus, dev)
+        node = int(open(path + "/numa_node").read().strip())
+        cpulist = open(path + "/local_cpulist").read().strip()
+        info["numa_node"] = node
+        if world > 1 and node >= 0 and cpulist:
+            cpus = set()
+            for part in cpulist.split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+            cpus &= set(os.sched_getaffinity(0))
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                info["cpus"] = len(cpus)
+    except Exception as e:  # noqa: BLE001
+        info["error"] = str(e)[:80]
+    return info
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -244,6 +272,7 @@ def main():
     from numericals_b200 import _lib
     from numericals_b200.array import from_pointer
 
+    affinity = bind_near_gpu(torch, local_rank, world)
     nu.require_device(local_rank)
     lib = _lib.lib()
     stream = torch.cuda.current_stream()
@@ -400,7 +429,8 @@ def main():
                        "sharding": "contiguous slab per rank, no data-path collective",
                        "l2": "inputs (1 GiB) and outputs (1 GiB) are each ~8x the 126 MB L2; no flush needed"},
             "hbm_gbs": value * 8.0, "per_ufunc": per_ufunc, "roofline": roofline, "e2e": e2e,
-            "gpu_launches": int(launches), "clocks": clocks, "cpu_baseline": cpu, "extra": extra,
+            "gpu_launches": int(launches), "clocks": clocks, "cpu_baseline": cpu, "host_affinity": affinity,
+            "extra": extra,
         }
         emit(line)
     if world > 1:

@@ -150,7 +150,7 @@ def _rank_main(rank, world, port, q):
 
 
 def test_process_per_gpu_sharded_arrays():
-    world = min(_ndev(), 4)
+    world = min(_ndev(), 8)
     if world < 2:
         pytest.skip("needs two devices")
     import torch.multiprocessing as mp
