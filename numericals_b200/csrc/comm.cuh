@@ -140,26 +140,50 @@ NUK_D void combine_allgather_body(const CommLink &L, size_t count, const typenam
   }
 }
 
-// all-reduce of `count` elements (count * sizeof(Acc-as-stored) <= kCommSlotBytes): CTA b owns the pieces
-// [b * per, (b+1) * per); out[i] = local_0[i] (+) local_1[i] (+) ... in rank order.
+// all-reduce of `count` elements (count * sizeof(T) <= kCommSlotBytes): CTA b owns the elements
+// [b * per, (b+1) * per), per a multiple of 16 / sizeof(T) that depends on `count` and the grid only -- every
+// rank cuts the payload the same way, because CTA b waits for exactly the pieces CTA b of its peers pushed.
+// out[i] = local_0[i] (+) local_1[i] (+) ... in rank order.  `vec`: this rank's local / out are 16-byte
+// aligned, so whole 16-byte groups move as one transfer (a per-rank choice: the slot layout is the same).
 template <class R>
-NUK_D void allreduce_body(const CommLink &L, int64_t count, const typename R::In *local, typename R::In *out) {
+NUK_D void allreduce_body(const CommLink &L, int64_t count, const typename R::In *local, typename R::In *out, int vec) {
   using T = typename R::In;
   using A = typename R::Acc;
+  constexpr int E = 16 / (int)sizeof(T);
   const int parity = (int)(L.seq & 1u);
-  const int64_t per = (count + gridDim.x - 1) / gridDim.x;
+  const int64_t groups = (count + E - 1) / E;
+  const int64_t per = ((groups + gridDim.x - 1) / gridDim.x) * E;
   const int64_t lo = (int64_t)blockIdx.x * per;
   const int64_t hi = (lo + per < count) ? lo + per : count;
+  const int64_t nv = (vec && hi > lo) ? (hi - lo) / E : 0;         // whole 16-byte groups of my piece
+  const int64_t tail = lo + nv * E;                                // elements [tail, hi) go one by one
   // phase 1: my piece into slot [rank] of every peer (own mailbox included), peers visited round-robin
   for (int k = 0; k < L.world; ++k) {
     const int p = (L.rank + k) % L.world;
     T *dst = reinterpret_cast<T *>(mail_data(L.mail[p], parity, L.rank));
-    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) dst[i] = local[i];
+    for (int64_t i = threadIdx.x; i < nv; i += blockDim.x)
+      reinterpret_cast<uint4 *>(dst + lo)[i] = reinterpret_cast<const uint4 *>(local + lo)[i];
+    for (int64_t i = tail + threadIdx.x; i < hi; i += blockDim.x) dst[i] = local[i];
   }
   if (!comm_exchange(L, (int)blockIdx.x)) return;
   // phase 2: fold the W pieces in rank order (L2 loads: the peers' stores bypass this SM's L1)
   char *mine = L.mail[L.rank];
-  for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+  for (int64_t i = threadIdx.x; i < nv; i += blockDim.x) {
+    Pack<T, E> v = ld_cg_any<Pack<T, E>>(reinterpret_cast<const uint4 *>(reinterpret_cast<const T *>(mail_data(mine, parity, 0)) + lo) + i);
+    A acc[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) acc[e] = R::load(v.v[e]);
+    for (int s = 1; s < L.world; ++s) {
+      v = ld_cg_any<Pack<T, E>>(reinterpret_cast<const uint4 *>(reinterpret_cast<const T *>(mail_data(mine, parity, s)) + lo) + i);
+#pragma unroll
+      for (int e = 0; e < E; ++e) acc[e] = R::combine(acc[e], R::load(v.v[e]));
+    }
+    Pack<T, E> r;
+#pragma unroll
+    for (int e = 0; e < E; ++e) r.v[e] = (T)acc[e];
+    reinterpret_cast<Pack<T, E> *>(out + lo)[i] = r;
+  }
+  for (int64_t i = tail + threadIdx.x; i < hi; i += blockDim.x) {
     A acc = R::load(ld_cg_any<T>(reinterpret_cast<const T *>(mail_data(mine, parity, 0)) + i));
     for (int s = 1; s < L.world; ++s)
       acc = R::combine(acc, R::load(ld_cg_any<T>(reinterpret_cast<const T *>(mail_data(mine, parity, s)) + i)));

@@ -55,6 +55,8 @@ inline bool on_host(PtrKind k) { return k == PK_HOST || k == PK_PAGEABLE; }
 
 // scratch memory private to (thread, device, stream): reduction partials etc.
 int scratch(cudaStream_t s, size_t bytes, void **dptr);
+// same, plus the arena's zero-initialised, self-re-arming arrival ticket (single-launch full reductions)
+int scratch_with_ticket(cudaStream_t s, size_t bytes, void **dptr, unsigned **ticket);
 // pinned result slot private to the thread (8 * 64 bytes, portable across devices)
 int pinned_slot(void **hptr);
 // small device buffers private to (thread, current device, slot), grown on demand

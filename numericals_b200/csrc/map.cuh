@@ -92,6 +92,20 @@ template <class F> NUK_D typename F::Out apply(const F &f, typename F::In a, typ
   if constexpr (F::kArity == 2) return f(a, b);
   else return f(a);
 }
+// The complete function where it is the RARE path of a split functor (re-doing a flagged element): called, not
+// inlined -- inlined once per element of a pack the special-case code is most of the kernel and pushes the hot
+// paths of neighbouring elements kilobytes apart in the instruction cache (NUK_RARE_CALL, A/B in profiles/).
+#ifndef NUK_RARE_CALL
+#define NUK_RARE_CALL 0
+#endif
+#if NUK_RARE_CALL
+template <class F> __device__ __noinline__ typename F::Out apply_rare(F f, typename F::In a, typename F::In b) {
+  if constexpr (F::kArity == 2) return f(a, b);
+  else return f(a);
+}
+#else
+template <class F> NUK_D typename F::Out apply_rare(const F &f, typename F::In a, typename F::In b) { return apply(f, a, b); }
+#endif
 
 // ------------------------------------------------------------------ flat kernel
 // MODE: 2 = one kernel for all-vector and scalar-operand tiles (default); a split functor is instantiated twice,
@@ -159,7 +173,7 @@ k_map_flat(size_t n, const typename F::In *x, const typename F::In *y, typename 
         if (any) {
 #pragma unroll
           for (int e = 0; e < E; ++e)
-            if (slow[e]) r.v[e] = apply(f, a[u].v[e], F::kArity == 2 ? b[u].v[e] : In());
+            if (slow[e]) r.v[e] = apply_rare(f, a[u].v[e], F::kArity == 2 ? b[u].v[e] : In());
         }
       } else {
 #pragma unroll
@@ -207,7 +221,7 @@ k_map_flat(size_t n, const typename F::In *x, const typename F::In *y, typename 
         if (any) {
 #pragma unroll
           for (int e = 0; e < E; ++e)
-            if (slow[e]) r.v[e] = apply(f, av[e], bv[e]);
+            if (slow[e]) r.v[e] = apply_rare(f, av[e], bv[e]);
         }
       } else {
 #pragma unroll
@@ -294,7 +308,7 @@ k_map_flat2(size_t n, int64_t ncols, const typename F::In *x, const typename F::
       if (any) {
 #pragma unroll
         for (int e = 0; e < E; ++e)
-          if (slow[e]) r.v[e] = apply(f, a.v[e], F::kArity == 2 ? b.v[e] : In());
+          if (slow[e]) r.v[e] = apply_rare(f, a.v[e], F::kArity == 2 ? b.v[e] : In());
       }
     } else {
 #pragma unroll
@@ -460,7 +474,7 @@ k_map_rows(RowsDesc d, const typename F::In *x, const typename F::In *y, typenam
           if (any) {
 #pragma unroll
             for (int e = 0; e < E; ++e)
-              if (slow[e]) rr.v[e] = apply(f, av[e], bv[e]);
+              if (slow[e]) rr.v[e] = apply_rare(f, av[e], bv[e]);
           }
         } else {
 #pragma unroll

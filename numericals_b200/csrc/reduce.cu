@@ -76,27 +76,46 @@ template <typename T> struct MomentsR {  // (sum x, sum x*x) in one pass
 // ---- 8/16-bit inputs: accumulate a whole 32-bit word per instruction (dp4a / dp2a for sums, packed
 // SIMD max/min for extrema) instead of extracting bytes; without this the narrow reductions are
 // issue-bound (i8sum 61%, i8hmax 50% of the HBM roofline in profiles/sweep_r01_a.jsonl).
+// The accumulator of a word lane is a pair of 32-bit registers (the 8-bit extrema keep even and odd bytes apart).
+struct WordAcc { uint32_t a, b; };
 template <class R> struct WordRed { static constexpr bool ok = false; };
 #define NUK_WORDRED(RED, IDENT, ACC_EXPR, FINISH_BODY)                                          \
   template <> struct WordRed<RED> {                                                             \
     static constexpr bool ok = true;                                                            \
     using A = typename RED::Acc;                                                                \
-    NUK_D static uint32_t identity() { return (IDENT); }                                        \
-    NUK_D static uint32_t acc(uint32_t a, uint32_t w) { return (ACC_EXPR); }                    \
-    NUK_D static A finish(A r, uint32_t a) { FINISH_BODY }                                      \
+    NUK_D static WordAcc identity() { return WordAcc{(IDENT), 0u}; }                            \
+    NUK_D static WordAcc acc(WordAcc s, uint32_t w) { const uint32_t a = s.a; return WordAcc{(ACC_EXPR), 0u}; } \
+    NUK_D static A finish(A r, WordAcc s) { const uint32_t a = s.a; FINISH_BODY }               \
   };
 NUK_WORDRED(SumR<int8_t>, 0u, (uint32_t)__dp4a((int)w, 0x01010101, (int)a), return r + a;)
 NUK_WORDRED(SumR<int16_t>, 0u, (uint32_t)__dp2a_lo((int)w, 0x00000101, (int)a), return r + a;)
-#define NUK_UNPACK4(T, OP) for (int k = 0; k < 4; ++k) { const T v = (T)(a >> (8 * k)); r = (v OP r) ? v : r; } return r;
 #define NUK_UNPACK2(T, OP) for (int k = 0; k < 2; ++k) { const T v = (T)(a >> (16 * k)); r = (v OP r) ? v : r; } return r;
-NUK_WORDRED(MaxR<int8_t>, 0x80808080u, __vmaxs4(a, w), NUK_UNPACK4(int8_t, >))
-NUK_WORDRED(MinR<int8_t>, 0x7f7f7f7fu, __vmins4(a, w), NUK_UNPACK4(int8_t, <))
-NUK_WORDRED(MaxR<uint8_t>, 0u, __vmaxu4(a, w), NUK_UNPACK4(uint8_t, >))
-NUK_WORDRED(MinR<uint8_t>, 0xffffffffu, __vminu4(a, w), NUK_UNPACK4(uint8_t, <))
 NUK_WORDRED(MaxR<int16_t>, 0x80008000u, __vmaxs2(a, w), NUK_UNPACK2(int16_t, >))
 NUK_WORDRED(MinR<int16_t>, 0x7fff7fffu, __vmins2(a, w), NUK_UNPACK2(int16_t, <))
 NUK_WORDRED(MaxR<uint16_t>, 0u, __vmaxu2(a, w), NUK_UNPACK2(uint16_t, >))
 NUK_WORDRED(MinR<uint16_t>, 0xffffffffu, __vminu2(a, w), NUK_UNPACK2(uint16_t, <))
+// 8-bit extrema: sm_100 has VIMNMX for 16-bit pairs but emulates the 4 x 8-bit forms in 6-7 instructions, so a word
+// is split into its even bytes (moved up: b0 00 b2 00 read as two 16-bit values = the bytes times 256, order and
+// sign preserved) and its odd bytes (masked in place), each folded with ONE 16x2 instruction (i8hmax / u8hmax: 0.82
+// -> of the HBM peak with __vmaxs4 / __vmaxu4).
+#define NUK_WORDRED8(RED, T, IDENT16, OP2, CMP)                                                  \
+  template <> struct WordRed<RED> {                                                             \
+    static constexpr bool ok = true;                                                            \
+    using A = typename RED::Acc;                                                                \
+    NUK_D static WordAcc identity() { return WordAcc{(IDENT16), (IDENT16)}; }                   \
+    NUK_D static WordAcc acc(WordAcc s, uint32_t w) {                                           \
+      return WordAcc{OP2(s.a, __byte_perm(w, 0u, 0x2404)), OP2(s.b, w & 0xff00ff00u)};          \
+    }                                                                                           \
+    NUK_D static A finish(A r, WordAcc s) {                                                     \
+      const uint32_t h[2] = {s.a, s.b};                                                         \
+      for (int k = 0; k < 4; ++k) { const T v = (T)(h[k >> 1] >> (8 + 16 * (k & 1))); r = (v CMP r) ? v : r; } \
+      return r;                                                                                 \
+    }                                                                                           \
+  };
+NUK_WORDRED8(MaxR<int8_t>, int8_t, 0x80008000u, __vmaxs2, >)
+NUK_WORDRED8(MinR<int8_t>, int8_t, 0x7f007f00u, __vmins2, <)
+NUK_WORDRED8(MaxR<uint8_t>, uint8_t, 0u, __vmaxu2, >)
+NUK_WORDRED8(MinR<uint8_t>, uint8_t, 0xff00ff00u, __vminu2, <)
 
 template <typename A> NUK_D A shfl_down(A v, int delta) {
   constexpr int W = (sizeof(A) + 3) / 4;
@@ -130,10 +149,46 @@ template <class R> NUK_D typename R::Acc block_reduce(typename R::Acc v, typenam
   return v;
 }
 
+// Pass 2 inside pass 1: every CTA publishes its partial, the LAST one to arrive (an atomic ticket) folds all of
+// them -- in index order through the block tree, so the result does not depend on which CTA that is -- and
+// re-arms the ticket.  One launch instead of two: a full reduction of a 256 MiB array is ~45 us of
+// streaming, and the second launch was ~4 us of it (8-bit sums / extrema: 0.82 -> of the HBM peak).
+template <class R>
+NUK_D void finish_in_last_cta(typename R::Acc v, typename R::Acc *partials, unsigned *ticket, typename R::In *o1,
+                              typename R::In *o2, typename R::Acc init, const typename R::In *first) {
+  using A = typename R::Acc;
+  __shared__ int last;
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x] = v;
+    __threadfence();
+    last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  A acc = init;
+  for (unsigned i = threadIdx.x; i < gridDim.x; i += kThreads) acc = R::combine(acc, ld_cg_any<A>(partials + i));
+  acc = block_reduce<R>(acc, init);
+  if (threadIdx.x == 0) {
+    // `first` (float extrema only): the element at index 0.  BMAS hmax / hmin fold from x[0]
+    // (oracle/bmas_oracle.c DEF_HMINMAX: r = x[0]; r = (a > r) ? a : r), so a NaN survives exactly when it sits
+    // in the FIRST position and is ignored anywhere else; the tree ignores every NaN, this puts the first one back.
+    if constexpr (std::is_floating_point<typename R::In>::value && std::is_same<A, typename R::In>::value) {
+      if (first) {
+        const typename R::In f0 = *first;
+        if (f0 != f0) acc = f0;
+      }
+    }
+    R::store(o1, o2, 0, acc);
+    *ticket = 0;
+  }
+}
+
 // ------------------------------------------------------------------ full, contiguous
 template <class R, int UNROLL>
 __global__ void __launch_bounds__(kThreads)
-k_reduce_flat(size_t n, const typename R::In *x, typename R::Acc *partials, typename R::Acc init) {
+k_reduce_flat(size_t n, const typename R::In *x, typename R::Acc *partials, typename R::Acc init, unsigned *ticket,
+              typename R::In *o1, typename R::In *o2, const typename R::In *first) {
   using T = typename R::In;
   using A = typename R::Acc;
   constexpr int E = 16 / sizeof(T);
@@ -145,7 +200,7 @@ k_reduce_flat(size_t n, const typename R::In *x, typename R::Acc *partials, type
   A acc[E];
 #pragma unroll
   for (int e = 0; e < E; ++e) acc[e] = init;
-  uint32_t wacc[4];
+  WordAcc wacc[4];
   if constexpr (WordRed<R>::ok) {
 #pragma unroll
     for (int w = 0; w < 4; ++w) wacc[w] = WordRed<R>::identity();
@@ -185,14 +240,16 @@ k_reduce_flat(size_t n, const typename R::In *x, typename R::Acc *partials, type
 #pragma unroll
   for (int e = 1; e < E; ++e) v = R::combine(v, acc[e]);
   v = block_reduce<R>(v, init);
-  if (threadIdx.x == 0) partials[blockIdx.x] = v;
+  if (ticket) finish_in_last_cta<R>(v, partials, ticket, o1, o2, init, first);
+  else if (threadIdx.x == 0) partials[blockIdx.x] = v;
 }
 
 // ------------------------------------------------------------------ full, strided nd
 template <class R>
 __global__ void __launch_bounds__(kThreads)
 k_reduce_nd(size_t n, NdDesc d, const typename R::In *x, typename R::Acc *partials,
-            typename R::Acc init) {
+            typename R::Acc init, unsigned *ticket, typename R::In *o1, typename R::In *o2,
+            const typename R::In *first) {
   using A = typename R::Acc;
   A acc = init;
   const size_t stride = (size_t)gridDim.x * kThreads;
@@ -208,33 +265,12 @@ k_reduce_nd(size_t n, NdDesc d, const typename R::In *x, typename R::Acc *partia
     acc = R::combine(acc, R::load(x[ox]));
   }
   acc = block_reduce<R>(acc, init);
-  if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+  if (ticket) finish_in_last_cta<R>(acc, partials, ticket, o1, o2, init, first);
+  else if (threadIdx.x == 0) partials[blockIdx.x] = acc;
 }
 
 // ------------------------------------------------------------------ pass 2
 // partials laid out [count][nout]; output j combines partials[0..count)[j] in index order.
-// `first` (float extrema only): the element at index 0.  BMAS hmax / hmin fold from x[0]
-// (oracle/bmas_oracle.c DEF_HMINMAX: r = x[0]; r = (a > r) ? a : r), so a NaN survives exactly when it
-// sits in the FIRST position and is ignored anywhere else; the tree ignores every NaN, this puts the
-// first one back.
-template <class R>
-__global__ void __launch_bounds__(kThreads)
-k_combine_one(size_t count, const typename R::Acc *partials, typename R::In *o1,
-              typename R::In *o2, typename R::Acc init, const typename R::In *first) {
-  using A = typename R::Acc;
-  A acc = init;
-  for (size_t i = threadIdx.x; i < count; i += kThreads) acc = R::combine(acc, partials[i]);
-  acc = block_reduce<R>(acc, init);
-  if (threadIdx.x == 0) {
-    if constexpr (std::is_floating_point<typename R::In>::value && std::is_same<A, typename R::In>::value) {
-      if (first) {
-        const typename R::In f0 = *first;
-        if (f0 != f0) acc = f0;
-      }
-    }
-    R::store(o1, o2, 0, acc);
-  }
-}
 template <class R>
 __global__ void __launch_bounds__(kThreads)
 k_combine_cols(int64_t count, int64_t nout, const typename R::Acc *partials, typename R::In *o1,
@@ -260,8 +296,8 @@ k_combine_allgather(CommLink link, size_t count, const typename R::Acc *partials
 }
 template <class R>
 __global__ void __launch_bounds__(kThreads)
-k_allreduce(CommLink link, int64_t count, const typename R::In *local, typename R::In *out) {
-  allreduce_body<R>(link, count, local, out);
+k_allreduce(CommLink link, int64_t count, const typename R::In *local, typename R::In *out, int vec) {
+  allreduce_body<R>(link, count, local, out, vec);
 }
 
 // ------------------------------------------------------------------ axis reductions
@@ -635,9 +671,11 @@ template <class R> static int run_full(const ReduceProblem &p, typename R::Acc i
   constexpr int E = 16 / sizeof(T);
   int grid;
   void *scratch_ptr = nullptr;
-  // pass-1 partials: the thread's arena, or the communicator's own buffer for a sharded reduction
+  unsigned *ticket = nullptr;   // non-null: ONE launch, the last CTA to arrive folds the partials (finish_in_last_cta)
+  // pass-1 partials: the thread's arena, or the communicator's own buffer for a sharded reduction (whose pass 2
+  // is the exchange kernel)
   auto partial_space = [&](size_t bytes, void **ptr) -> int {
-    if (!p.link) return scratch(p.stream, bytes, ptr);
+    if (!p.link) return scratch_with_ticket(p.stream, bytes, ptr, &ticket);
     if (bytes > p.link_partial_bytes) {
       set_error(NUK_ERR_INVALID, "internal: communicator partial buffer too small (%zu > %zu)", bytes,
                 p.link_partial_bytes);
@@ -646,11 +684,13 @@ template <class R> static int run_full(const ReduceProblem &p, typename R::Acc i
     *ptr = p.link_partials;
     return NUK_OK;
   };
+  const T *first = ((p.red == NUK_HMAX || p.red == NUK_HMIN) && !(p.flags & NUK_REDUCE_NO_SEED) && n > 0) ? x : nullptr;
   if (contig && aligned_to(x, 16)) {
     const size_t tiles = n / E / ((size_t)kThreads * UNROLL) + 1;
     grid = grid_for(tiles, (int)opt(OPT_REDUCE_GRID_MULT));
     NUK_TRY(partial_space(sizeof(A) * (size_t)grid, &scratch_ptr));
-    k_reduce_flat<R, UNROLL><<<grid, kThreads, 0, p.stream>>>(n, x, static_cast<A *>(scratch_ptr), init);
+    k_reduce_flat<R, UNROLL><<<grid, kThreads, 0, p.stream>>>(n, x, static_cast<A *>(scratch_ptr), init, ticket, o1, o2,
+                                                              first);
     NUK_TRY(post_launch("k_reduce_flat"));
   } else {
     NdDesc d;
@@ -664,18 +704,15 @@ template <class R> static int run_full(const ReduceProblem &p, typename R::Acc i
     const size_t blocks = (n + kThreads * 4 - 1) / (kThreads * 4);
     grid = grid_for(blocks ? blocks : 1, (int)opt(OPT_REDUCE_GRID_MULT));
     NUK_TRY(partial_space(sizeof(A) * (size_t)grid, &scratch_ptr));
-    k_reduce_nd<R><<<grid, kThreads, 0, p.stream>>>(n, d, x, static_cast<A *>(scratch_ptr), init);
+    k_reduce_nd<R><<<grid, kThreads, 0, p.stream>>>(n, d, x, static_cast<A *>(scratch_ptr), init, ticket, o1, o2, first);
     NUK_TRY(post_launch("k_reduce_nd"));
   }
-  const T *first = ((p.red == NUK_HMAX || p.red == NUK_HMIN) && !(p.flags & NUK_REDUCE_NO_SEED) && n > 0) ? x : nullptr;
   if (p.link) {
     k_combine_allgather<R><<<1, kThreads, 0, p.stream>>>(*p.link, (size_t)grid, static_cast<const A *>(scratch_ptr), o1,
                                                          o2, init, first);
     return post_launch("k_combine_allgather");
   }
-  k_combine_one<R><<<1, kThreads, 0, p.stream>>>((size_t)grid, static_cast<const A *>(scratch_ptr), o1, o2, init,
-                                                 first);
-  return post_launch("k_combine_one");
+  return NUK_OK;
 }
 
 template <class R> static int run_axis(const ReduceProblem &p, typename R::Acc init) {
@@ -906,16 +943,18 @@ template <typename T> static int allreduce_typed(const CommLink &link, int red, 
                                                  void *out, cudaStream_t stream) {
   // enough CTAs to keep the NVLink stores in flight, never more than the flag table holds; a function of
   // `count` only, so every rank launches the same grid
-  int64_t g = (count * (int64_t)sizeof(T) + 8191) / 8192;
+  int64_t g = (count * (int64_t)sizeof(T) + 2047) / 2048;     // 2 KB (128 threads x 16 B) per CTA and peer
   if (g < 1) g = 1;
   if (g > kCommMaxCtas) g = kCommMaxCtas;
   const T *l = static_cast<const T *>(local);
   T *o = static_cast<T *>(out);
+  // a per-rank choice (the cut of the payload into CTA pieces does not depend on it, comm.cuh)
+  const int vec = (aligned_to(local, 16) && aligned_to(out, 16)) ? 1 : 0;
   switch (red) {
     case NUK_SUM:
-    case NUK_SUMSQ: k_allreduce<SumR<T>><<<(unsigned)g, kThreads, 0, stream>>>(link, count, l, o); break;
-    case NUK_HMAX: k_allreduce<MaxR<T>><<<(unsigned)g, kThreads, 0, stream>>>(link, count, l, o); break;
-    case NUK_HMIN: k_allreduce<MinR<T>><<<(unsigned)g, kThreads, 0, stream>>>(link, count, l, o); break;
+    case NUK_SUMSQ: k_allreduce<SumR<T>><<<(unsigned)g, kThreads, 0, stream>>>(link, count, l, o, vec); break;
+    case NUK_HMAX: k_allreduce<MaxR<T>><<<(unsigned)g, kThreads, 0, stream>>>(link, count, l, o, vec); break;
+    case NUK_HMIN: k_allreduce<MinR<T>><<<(unsigned)g, kThreads, 0, stream>>>(link, count, l, o, vec); break;
     default:
       set_error(NUK_ERR_UNSUPPORTED, "all-reduce: unknown reduction %d", red);
       return NUK_ERR_UNSUPPORTED;

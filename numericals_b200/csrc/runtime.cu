@@ -211,22 +211,40 @@ struct ThreadState {
 };
 static thread_local ThreadState tl_state;
 
-int scratch(cudaStream_t s, size_t bytes, void **dptr) {
+// Every arena starts with a 256-byte header that is zero when a kernel starts: the arrival ticket of the
+// single-launch full reductions (reduce.cu: finish_in_last_cta, which re-arms it).  scratch() hands out the
+// memory after the header.
+constexpr size_t kArenaHeader = 256;
+static int arena_for(cudaStream_t s, size_t bytes, Arena **out) {
   const DeviceInfo *d = device_info();
   if (!d) return nuk_last_status();
   Arena &a = tl_state.arenas[ArenaKey{d->device, s}];
-  if (a.bytes < bytes) {
+  if (a.bytes < bytes + kArenaHeader) {
     if (a.ptr) {
       NUK_CUDA(cudaStreamSynchronize(s));  // earlier kernels may still read the old arena
       NUK_CUDA(cudaFree(a.ptr));
       a.ptr = nullptr;
       a.bytes = 0;
     }
-    size_t want = bytes < (1u << 20) ? (1u << 20) : bytes;
+    size_t want = bytes + kArenaHeader < (1u << 20) ? (1u << 20) : bytes + kArenaHeader;
     NUK_CUDA(cudaMalloc(&a.ptr, want));
+    NUK_CUDA(cudaMemsetAsync(a.ptr, 0, kArenaHeader, s));
     a.bytes = want;
   }
-  *dptr = a.ptr;
+  *out = &a;
+  return NUK_OK;
+}
+int scratch(cudaStream_t s, size_t bytes, void **dptr) {
+  Arena *a = nullptr;
+  NUK_TRY(arena_for(s, bytes, &a));
+  *dptr = static_cast<char *>(a->ptr) + kArenaHeader;
+  return NUK_OK;
+}
+int scratch_with_ticket(cudaStream_t s, size_t bytes, void **dptr, unsigned **ticket) {
+  Arena *a = nullptr;
+  NUK_TRY(arena_for(s, bytes, &a));
+  *dptr = static_cast<char *>(a->ptr) + kArenaHeader;
+  *ticket = static_cast<unsigned *>(a->ptr);
   return NUK_OK;
 }
 

@@ -68,8 +68,24 @@ NUK_F32_UNARY(LogF, log_f32)
 NUK_F32_UNARY_U(ExpF, exp_f32, 2)   // 5.9 TB/s with 2 packs per thread vs 5.2 with 4 (profiles/membench_r01.txt)
 NUK_F32_UNARY_FAST(TanF, tan_f32, NUK_F32_UNROLL, 0, NUK_FAST_TRIG32) NUK_F32_VIA_F64(AsinF, asin_f32) NUK_F32_VIA_F64(AcosF, acos_f32)
 NUK_F32_VIA_F64(AtanF, atan_f32) NUK_F32_UNARY_FAST(SinhF, sinh_f32, NUK_F32_UNROLL, 0, NUK_FAST_HYP32) NUK_F32_UNARY_FAST(CoshF, cosh_f32, NUK_F32_UNROLL, 0, NUK_FAST_HYP32)
-NUK_F32_UNARY_FAST(AsinhF, asinh_f32, NUK_F32_UNROLL, 0, NUK_FAST_HYP32) NUK_F32_UNARY_FAST(AcoshF, acosh_f32, NUK_F32_UNROLL, 0, NUK_FAST_HYP32)
-NUK_F32_UNARY_FAST(AtanhF, atanh_f32, NUK_F32_UNROLL, 0, NUK_FAST_HYP32)
+// asinh / acosh / atanh: double arithmetic on the 640 bytes of single-float pow tables (nukmath_tab.cuh)
+#ifndef NUK_HYPINV32_MINB
+#define NUK_HYPINV32_MINB 0
+#endif
+#ifndef NUK_HYPINV32_UNROLL
+#define NUK_HYPINV32_UNROLL 2
+#endif
+#define NUK_F32_UNARY_TAB(Name, FN)                     \
+  struct Name : TabPowF {                               \
+    using In = float; using Out = float;                \
+    static constexpr int kArity = 1;                    \
+    static constexpr int kMapUnroll = NUK_HYPINV32_UNROLL; \
+    static constexpr int kMapMinBlocks = NUK_HYPINV32_MINB; \
+    static constexpr bool kHasFast = true;              \
+    NUK_D float operator()(float a) const { return nukmath::FN(a, tab); } \
+    NUK_D float fast(float a, bool &slow) const { return nukmath::FN##_fast(a, tab, slow); } \
+  };
+NUK_F32_UNARY_TAB(AsinhF, asinh_f32) NUK_F32_UNARY_TAB(AcoshF, acosh_f32) NUK_F32_UNARY_TAB(AtanhF, atanh_f32)
 struct Atan2F {
   using In = float; using Out = float;
   static constexpr int kArity = 2;
