@@ -83,6 +83,18 @@ template <class F> struct HasFast<F, std::void_t<decltype(F::kHasFast)>> { stati
 // ... and may keep the per-element form for its scalar-operand tiles (kScalarSplit = false: pow f32 spills there)
 template <class F, class = void> struct ScalarSplit { static constexpr bool value = true; };
 template <class F> struct ScalarSplit<F, std::void_t<decltype(F::kScalarSplit)>> { static constexpr bool value = F::kScalarSplit; };
+// kWarpSplit: the same fast() / operator() pair, split per WARP instead of per pack: every element evaluates the
+// branch-free fast() and the warp votes; only if some lane raised `slow` does the whole warp call the complete
+// function (a real CALL).  The branch on a vote is uniform, so the hot path carries no BSSY / BSYNC pair and no
+// jump to a join point -- two instructions fewer per element than the per-element `if (rare)` form (tanh f32:
+// 43 -> 41), without keeping a pack's inputs and flags alive as the pack-level split does.  Only used in the
+// all-vector tile of the flat kernel, where all 32 lanes of a warp are converged by construction.
+template <class F, class = void> struct WarpSplit { static constexpr bool value = false; };
+template <class F> struct WarpSplit<F, std::void_t<decltype(F::kWarpSplit)>> { static constexpr bool value = F::kWarpSplit; };
+template <class F> __device__ __noinline__ typename F::Out apply_called(F f, typename F::In a, typename F::In b) {
+  if constexpr (F::kArity == 2) return f(a, b);
+  else return f(a);
+}
 template <class F> NUK_D typename F::Out apply_fast(const F &f, typename F::In a, typename F::In b, bool &slow) {
   if constexpr (F::kArity == 2) return f.fast(a, b, slow);
   else return f.fast(a, slow);
@@ -162,6 +174,13 @@ k_map_flat(size_t n, const typename F::In *x, const typename F::In *y, typename 
 #pragma unroll
         for (int w = 0; w < 4; ++w) wr[w] = Word4<F>::op(wa[w], wb[w]);
         memcpy(&r, wr, 16);
+      } else if constexpr (WarpSplit<F>::value) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          bool slow = false;
+          r.v[e] = apply_fast(f, a[u].v[e], F::kArity == 2 ? b[u].v[e] : In(), slow);
+          if (__any_sync(0xffffffffu, slow)) r.v[e] = apply_called(f, a[u].v[e], F::kArity == 2 ? b[u].v[e] : In());
+        }
       } else if constexpr (HasFast<F>::value) {
         bool slow[E], any = false;
 #pragma unroll

@@ -23,7 +23,8 @@ namespace nuk {
     static constexpr int kArity = 1;                    \
     static constexpr int kMapUnroll = UNR;              \
     static constexpr int kMapMinBlocks = MINB;          \
-    static constexpr bool kHasFast = ON;                \
+    static constexpr bool kHasFast = (ON) == 1;         \
+    static constexpr bool kWarpSplit = (ON) == 2;       /* 2: per-warp vote + called rare path (map.cuh) */ \
     NUK_D float operator()(float a) const { return nukmath::FN(a); } \
     NUK_D float fast(float a, bool &slow) const { return nukmath::FN##_fast(a, slow); } \
   };
@@ -31,10 +32,10 @@ namespace nuk {
 #define NUK_F32_MINB 5
 #endif
 #ifndef NUK_FAST_TRIG32
-#define NUK_FAST_TRIG32 false   // measured slower with the split (profiles/fast_split_ab_r01.txt)
+#define NUK_FAST_TRIG32 2   // 0 per-element branches, 1 pack-level split (slower: profiles/fast_split_ab_r01.txt), 2 per-warp vote + called rare path (profiles/ab_warp_r02.txt: sin 0.955 -> 0.979, cos 0.962 -> 0.999 of the measured HBM peak)
 #endif
 #ifndef NUK_FAST_HYP32
-#define NUK_FAST_HYP32 true    // sinh cosh asinh acosh atanh: +2..3 points with the split and no register cap
+#define NUK_FAST_HYP32 1    // sinh cosh asinh acosh atanh: +2..3 points with the split and no register cap
 #endif
 #ifndef NUK_FAST_ATAN2F
 #define NUK_FAST_ATAN2F false   // measured slower with the split (profiles/fast_split_ab_r01.txt)
@@ -52,15 +53,14 @@ namespace nuk {
     static constexpr int kMapUnroll = 2;                \
     NUK_D float operator()(float a, float b) const { return nukmath::FN(a, b); } \
   };
-// sin / cos capped at 32 registers (cos 92 -> 97 %, profiles/minblocks_sweep_r01.txt)
 #ifndef NUK_FAST_TANH32
-#define NUK_FAST_TANH32 false
+#define NUK_FAST_TANH32 2
 #endif
 #ifndef NUK_TANH32_MINB
 #define NUK_TANH32_MINB 0
 #endif
 #ifndef NUK_TRIG32_MINB
-#define NUK_TRIG32_MINB 8
+#define NUK_TRIG32_MINB 0   // the 32-register cap of round 1 makes the warp-split form spill around the call
 #endif
 NUK_F32_UNARY_FAST(SinF, sin_f32, 4, NUK_TRIG32_MINB, NUK_FAST_TRIG32) NUK_F32_UNARY_FAST(CosF, cos_f32, 4, NUK_TRIG32_MINB, NUK_FAST_TRIG32)
 NUK_F32_UNARY_FAST(TanhF, tanh_f32, 4, NUK_TANH32_MINB, NUK_FAST_TANH32)
