@@ -90,7 +90,11 @@ template <class F> struct ScalarSplit<F, std::void_t<decltype(F::kScalarSplit)>>
 // 43 -> 41), without keeping a pack's inputs and flags alive as the pack-level split does.  Only used in the
 // all-vector tile of the flat kernel, where all 32 lanes of a warp are converged by construction.
 template <class F, class = void> struct WarpSplit { static constexpr bool value = false; };
+#if defined(NUK_WARP_SPLIT_ALL)   // A/B: every split functor of the translation unit takes the per-warp form
+template <class F> struct WarpSplit<F, std::void_t<decltype(F::kHasFast)>> { static constexpr bool value = F::kHasFast; };
+#else
 template <class F> struct WarpSplit<F, std::void_t<decltype(F::kWarpSplit)>> { static constexpr bool value = F::kWarpSplit; };
+#endif
 template <class F> __device__ __noinline__ typename F::Out apply_called(F f, typename F::In a, typename F::In b) {
   if constexpr (F::kArity == 2) return f(a, b);
   else return f(a);
