@@ -11,12 +11,15 @@ rank owns one 2^28-element slab of an (N * 2^28)-element array (weak scaling, no
 collective: elementwise maps shard by contiguous slabs).
 
   value      Gelem/s over the whole job, inputs resident in HBM (arrays are 1 GiB: larger than L2)
-  e2e        same metric through the reference-facing BMAS_s<fn> symbols with HOST (pinned)
-             buffers: chunked H2D -> kernel -> D2H inside the timed region
+  e2e        same metric through the reference-facing BMAS_s<fn> symbols with HOST (page-locked)
+             buffers: chunked H2D -> kernel -> D2H inside the timed region; e2e.pageable: the same
+             calls on plain (pageable) numpy buffers, which is what a Lisp heap vector is
   roofline   dominant kernel (the slowest of the four maps): algorithmic 8 B/element x 2^28 / its
              CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs
   cpu_baseline  the oracle (BMAS contract restated over SLEEF u10) timed on this box's host cores
-  extra      C1 / C3 / C4 / C5 of BASELINE.json configs, each with its own algorithmic GB/s
+  extra      C1 / C3 / C4 / C5 of BASELINE.json configs, each with its own algorithmic GB/s; C5 and the sharded
+             C4 go through libnuk's own communicator (include/nuk.h "multi-GPU"): torch.distributed only
+             carries the 128-byte handles, barriers and the max-over-ranks of the timings
 
 Nothing here reads /root/reference.  The oracle is only executed by cpu_baseline and --impl reference.
 """

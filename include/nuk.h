@@ -159,7 +159,8 @@ int nuk_graph_launch(nuk_graph_t g, nuk_stream_t s);
 int nuk_graph_destroy(nuk_graph_t g);
 
 /* knobs (also readable from the environment at first use: NUK_GRID_MULT, NUK_STAGE_MB, ...).
- * NUK_LOG=1 in the environment prints one line per kernel launch to stderr. */
+ * NUK_LOG=1 in the environment prints one line per kernel launch to stderr; NUK_NVTX=1 wraps every entry point
+ * in an NVTX range ("BMAS/map", "BMAS/reduce", "nuk/map2", "nuk/reduce", "nuk/comm_reduce" ...). */
 int nuk_set_option(const char *name, long value);
 long nuk_get_option(const char *name);
 /* number of kernels launched by this library since load (all threads) */

@@ -21,6 +21,7 @@ static void host_scalar(const Opnd &o, Scalar64 *v) {
 // Launch = int(const MapProblem&)
 template <class Launch>
 static int run_map_1d(int arity, long n, Opnd x, Opnd y, Opnd out, Launch launch) {
+  ApiRange range("BMAS/map");
   nuk_clear_error();  // nuk_last_status() describes the most recent BMAS_* call of this thread
   const DeviceInfo *dev = device_info();
   if (!dev) return nuk_last_status();
@@ -110,6 +111,7 @@ static int run_map_1d(int arity, long n, Opnd x, Opnd y, Opnd out, Launch launch
 
 // ------------------------------------------------------------------ reductions by value
 static int reduce_value(int red, int dtype, long n, const void *x, long incx, void *result) {
+  ApiRange range("BMAS/reduce");
   nuk_clear_error();
   const size_t sz = dtype_size(dtype);
   memset(result, 0, sz);   // a defined value even when the call fails (BMAS returns by value, no error channel)

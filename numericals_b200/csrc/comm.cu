@@ -282,6 +282,7 @@ NUK_API int nuk_comm_status(nuk_comm_t c) {
 // ------------------------------------------------------------------ collectives
 NUK_API int nuk_comm_allreduce(nuk_comm_t c, int red, int dtype, int64_t count, const void *local, void *out,
                                nuk_stream_t s) {
+  ApiRange range("nuk/comm_allreduce");
   NUK_TRY(check_ready(c));
   const size_t sz = dtype_size(dtype);
   if (!sz || count < 0 || (count > 0 && (!local || !out))) {
@@ -305,6 +306,7 @@ NUK_API int nuk_comm_allreduce(nuk_comm_t c, int red, int dtype, int64_t count, 
 // that folds the partials, exchanges the value over peer memory and folds the W values (comm.cuh)
 static int comm_reduce_entry(nuk_comm_t c, int red, int dtype, int rank, const int64_t *dims, const int64_t *sx,
                              const void *x, void *out, void *out2, nuk_stream_t s) {
+  ApiRange range("nuk/comm_reduce");
   NUK_TRY(check_ready(c));
   if (rank < 0 || rank > NUK_MAX_RANK || !x || !out) {
     set_error(NUK_ERR_INVALID, "nuk_comm_reduce: bad descriptor (rank %d)", rank);

@@ -38,6 +38,13 @@ int use_device(int dev);              // make `dev` the calling thread's device 
 cudaStream_t current_stream();        // thread-local stream used by BMAS_* symbols
 void count_launch(unsigned n = 1);    // gpu_launches bookkeeping
 int post_launch(const char *kernel);  // cudaGetLastError -> status (+ the NUK_LOG per-launch line)
+// NVTX range around an entry point of the C ABI (NUK_NVTX=1 in the environment; otherwise one predictable branch):
+// lets `ncu --nvtx --nvtx-include "BMAS/"` or a timeline tool cut a host program's calls out of everything else
+struct ApiRange {
+  bool on;
+  explicit ApiRange(const char *name);
+  ~ApiRange();
+};
 
 // NUK_* knobs: lock-free reads on the launch path (nuk_set_option / the environment write them)
 enum Opt {

@@ -179,12 +179,26 @@ k_map_flat(size_t n, const typename F::In *x, const typename F::In *y, typename 
         for (int w = 0; w < 4; ++w) wr[w] = Word4<F>::op(wa[w], wb[w]);
         memcpy(&r, wr, 16);
       } else if constexpr (WarpSplit<F>::value) {
+#if defined(NUK_WARP_PACK)   // A/B: one vote per pack instead of one per element
+        bool slow = false;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          bool s1 = false;
+          r.v[e] = apply_fast(f, a[u].v[e], F::kArity == 2 ? b[u].v[e] : In(), s1);
+          slow |= s1;
+        }
+        if (__any_sync(0xffffffffu, slow)) {
+#pragma unroll
+          for (int e = 0; e < E; ++e) r.v[e] = apply_called(f, a[u].v[e], F::kArity == 2 ? b[u].v[e] : In());
+        }
+#else
 #pragma unroll
         for (int e = 0; e < E; ++e) {
           bool slow = false;
           r.v[e] = apply_fast(f, a[u].v[e], F::kArity == 2 ? b[u].v[e] : In(), slow);
           if (__any_sync(0xffffffffu, slow)) r.v[e] = apply_called(f, a[u].v[e], F::kArity == 2 ? b[u].v[e] : In());
         }
+#endif
       } else if constexpr (HasFast<F>::value) {
         bool slow[E], any = false;
 #pragma unroll

@@ -134,6 +134,7 @@ using namespace nuk;
 NUK_API int nuk_map2(int op, int dtype, int rank, const int64_t *dims, const int64_t *sx,
                      const int64_t *sy, const int64_t *so, const void *x, const void *y, void *out,
                      nuk_stream_t s) {
+  ApiRange range("nuk/map2");
   NUK_TRY(check_ptrs(out, x, 1));
   NUK_TRY(check_ptrs(out, y, 1));
   const size_t sz = dtype_size(dtype);
@@ -144,6 +145,7 @@ NUK_API int nuk_map2(int op, int dtype, int rank, const int64_t *dims, const int
 
 NUK_API int nuk_map1(int op, int dtype, int rank, const int64_t *dims, const int64_t *sx,
                      const int64_t *so, const void *x, void *out, nuk_stream_t s) {
+  ApiRange range("nuk/map1");
   NUK_TRY(check_ptrs(out, x, 1));
   const size_t sz = dtype_size(dtype);
   MapProblem p;
@@ -154,6 +156,7 @@ NUK_API int nuk_map1(int op, int dtype, int rank, const int64_t *dims, const int
 NUK_API int nuk_cmp2(int cmp, int dtype, int rank, const int64_t *dims, const int64_t *sx,
                      const int64_t *sy, const int64_t *so, const void *x, const void *y,
                      uint8_t *out, nuk_stream_t s) {
+  ApiRange range("nuk/cmp2");
   NUK_TRY(check_ptrs(out, x, 1));
   NUK_TRY(check_ptrs(out, y, 1));
   MapProblem p;
@@ -163,6 +166,7 @@ NUK_API int nuk_cmp2(int cmp, int dtype, int rank, const int64_t *dims, const in
 
 NUK_API int nuk_cast(int src_dtype, int dst_dtype, int rank, const int64_t *dims, const int64_t *sx,
                      const int64_t *so, const void *x, void *out, nuk_stream_t s) {
+  ApiRange range("nuk/cast");
   NUK_TRY(check_ptrs(out, x, 1));
   MapProblem p;
   NUK_TRY(make_problem(&p, 1, dtype_size(src_dtype), dtype_size(dst_dtype), rank, dims, sx, nullptr,
@@ -173,6 +177,7 @@ NUK_API int nuk_cast(int src_dtype, int dst_dtype, int rank, const int64_t *dims
 NUK_API int nuk_map2_scalar(int op, int dtype, int rank, const int64_t *dims, const int64_t *sa,
                             const int64_t *so, const void *a, const void *host_scalar,
                             int scalar_is_x, void *out, nuk_stream_t s) {
+  ApiRange range("nuk/map2_scalar");
   NUK_TRY(check_ptrs(out, a, 1));
   Scalar64 v;
   NUK_TRY(load_scalar(dtype, host_scalar, &v));
@@ -191,6 +196,7 @@ NUK_API int nuk_map2_scalar(int op, int dtype, int rank, const int64_t *dims, co
 NUK_API int nuk_cmp2_scalar(int cmp, int dtype, int rank, const int64_t *dims, const int64_t *sa,
                             const int64_t *so, const void *a, const void *host_scalar,
                             int scalar_is_x, uint8_t *out, nuk_stream_t s) {
+  ApiRange range("nuk/cmp2_scalar");
   NUK_TRY(check_ptrs(out, a, 1));
   Scalar64 v;
   NUK_TRY(load_scalar(dtype, host_scalar, &v));
@@ -208,6 +214,7 @@ NUK_API int nuk_cmp2_scalar(int cmp, int dtype, int rank, const int64_t *dims, c
 
 NUK_API int nuk_fill(int dtype, int rank, const int64_t *dims, const int64_t *so,
                      const void *host_scalar, void *out, nuk_stream_t s) {
+  ApiRange range("nuk/fill");
   NUK_TRY(check_ptrs(out, nullptr, 0));
   Scalar64 v;
   NUK_TRY(load_scalar(dtype, host_scalar, &v));

@@ -1010,6 +1010,7 @@ using namespace nuk;
 static int reduce_entry(int red, int dtype, int rank, const int64_t *dims, const int64_t *sx, int axis,
                         const int64_t *so, const void *x, void *out, void *out2, int flags,
                         nuk_stream_t s) {
+  ApiRange range("nuk/reduce");
   if (rank < 0 || rank > NUK_MAX_RANK || !x || !out || axis >= rank) {
     set_error(NUK_ERR_INVALID, "bad reduce descriptor (rank %d, axis %d)", rank, axis);
     return NUK_ERR_INVALID;

@@ -9,6 +9,7 @@
 #include <string>
 #include <unordered_map>
 #include <vector>
+#include <nvtx3/nvToolsExt.h>
 #include "common.cuh"
 
 namespace nuk {
@@ -103,6 +104,20 @@ static int log_level() {
     return v ? atoi(v) : 0;
   }();
   return lv;
+}
+
+static bool nvtx_on() {
+  static const bool on = [] {
+    const char *v = getenv("NUK_NVTX");
+    return v && atoi(v) != 0;
+  }();
+  return on;
+}
+ApiRange::ApiRange(const char *name) : on(nvtx_on()) {
+  if (on) nvtxRangePushA(name);
+}
+ApiRange::~ApiRange() {
+  if (on) nvtxRangePop();
 }
 
 int post_launch(const char *kernel) {

@@ -62,11 +62,11 @@ class Communicator:
     def from_process_group(cls, dist, rank, world):
         """one process per GPU: create on the current device, exchange the handles through `dist`"""
         from . import _lib as L
-        import torch
         lib = L.lib()
         h = _vp()
         L.check(lib.nuk_comm_create(world, rank, C.byref(h)))
         if world > 1:
+            import torch
             mine = (C.c_ubyte * L.COMM_HANDLE_BYTES)()
             L.check(lib.nuk_comm_export(h, mine))
             dev = "cuda" if dist.get_backend() == "nccl" else "cpu"

@@ -268,3 +268,22 @@ def test_contiguous_out_with_broadcast_operands_flat2(prefix, ncols, nu, libnuk,
     t3 = rnd(rng, dt, (3, 7, ncols))
     got = nu.multiply(nu.asarray(t3, type=et), dev["vec"]).to_numpy()
     assert same(got, refnu.two_arg("mul", t3, kinds["vec"]))
+
+
+def test_flat2_writes_only_its_block(nu, refnu):
+    """OUT is a contiguous block INSIDE a larger array (rows 3..40 of a matrix): k_map_flat2 must leave the rows
+    before and after it alone -- tile remainders, the last ragged tile and the column-vector prefetch included
+    (compute-sanitizer is closed on this GPU pool; whole-buffer comparisons stand in for memcheck)."""
+    rng = np.random.default_rng(33)
+    for dt, et, ncols in ((np.float32, "single-float", 1028), (np.float64, "double-float", 1030), (np.uint8, "(unsigned-byte 8)", 4112)):
+        big = rnd(rng, dt, (50, ncols))
+        m = rnd(rng, dt, (50, ncols))
+        v, c = rnd(rng, dt, (ncols,)), rnd(rng, dt, (50, 1))
+        dbig, dm = nu.asarray(big, type=et), nu.asarray(m, type=et)
+        nu.multiply(dm[3:40], nu.asarray(v, type=et), out=dbig[3:40])
+        want = big.copy()
+        want[3:40] = refnu.two_arg("mul", m[3:40], v)
+        assert same(dbig.to_numpy(), want), (et, "row vector")
+        nu.two_arg_max(dm[3:40], nu.asarray(c, type=et)[3:40], out=dbig[3:40])
+        want[3:40] = refnu.two_arg("max", np.ascontiguousarray(m[3:40]), np.ascontiguousarray(c[3:40]))
+        assert same(dbig.to_numpy(), want), (et, "column vector")
