@@ -62,11 +62,22 @@ namespace nuk {
 #ifndef NUK_TRIG32_MINB
 #define NUK_TRIG32_MINB 0   // the 32-register cap of round 1 makes the warp-split form spill around the call
 #endif
-NUK_F32_UNARY_FAST(SinF, sin_f32, 4, NUK_TRIG32_MINB, NUK_FAST_TRIG32) NUK_F32_UNARY_FAST(CosF, cos_f32, 4, NUK_TRIG32_MINB, NUK_FAST_TRIG32)
-NUK_F32_UNARY_FAST(TanhF, tanh_f32, 4, NUK_TANH32_MINB, NUK_FAST_TANH32)
+// packs per thread (profiles/ab_unroll_r02.txt): sin / cos 8 (32 elements per thread: 0.335 -> 0.312 ms, 0.336 -> 0.309 ms
+// per 2^28 -- 105 / 106 % of the measured HBM peak), tanh 4 (8: 0.360 -> 0.368 ms)
+#ifndef NUK_TRIG32_UNROLL
+#define NUK_TRIG32_UNROLL 8
+#endif
+#ifndef NUK_TANH32_UNROLL
+#define NUK_TANH32_UNROLL 4
+#endif
+#ifndef NUK_TAN32_UNROLL
+#define NUK_TAN32_UNROLL NUK_F32_UNROLL
+#endif
+NUK_F32_UNARY_FAST(SinF, sin_f32, NUK_TRIG32_UNROLL, NUK_TRIG32_MINB, NUK_FAST_TRIG32) NUK_F32_UNARY_FAST(CosF, cos_f32, NUK_TRIG32_UNROLL, NUK_TRIG32_MINB, NUK_FAST_TRIG32)
+NUK_F32_UNARY_FAST(TanhF, tanh_f32, NUK_TANH32_UNROLL, NUK_TANH32_MINB, NUK_FAST_TANH32)
 NUK_F32_UNARY(LogF, log_f32)
 NUK_F32_UNARY_U(ExpF, exp_f32, 2)   // 5.9 TB/s with 2 packs per thread vs 5.2 with 4 (profiles/membench_r01.txt)
-NUK_F32_UNARY_FAST(TanF, tan_f32, NUK_F32_UNROLL, 0, NUK_FAST_TRIG32) NUK_F32_VIA_F64(AsinF, asin_f32) NUK_F32_VIA_F64(AcosF, acos_f32)
+NUK_F32_UNARY_FAST(TanF, tan_f32, NUK_TAN32_UNROLL, 0, NUK_FAST_TRIG32) NUK_F32_VIA_F64(AsinF, asin_f32) NUK_F32_VIA_F64(AcosF, acos_f32)
 NUK_F32_VIA_F64(AtanF, atan_f32) NUK_F32_UNARY_FAST(SinhF, sinh_f32, NUK_F32_UNROLL, 0, NUK_FAST_HYP32) NUK_F32_UNARY_FAST(CoshF, cosh_f32, NUK_F32_UNROLL, 0, NUK_FAST_HYP32)
 // asinh / acosh / atanh: double arithmetic on the 640 bytes of single-float pow tables (nukmath_tab.cuh)
 #ifndef NUK_HYPINV32_MINB

@@ -190,3 +190,41 @@ def test_process_per_gpu_sharded_arrays():
     assert np.allclose(np.frombuffer(mats[0][6]), p.var(axis=0, ddof=1), rtol=1e-9)
     assert np.allclose(np.frombuffer(b"".join(m[7] for m in mats)), p.var(axis=1), rtol=1e-9)
     assert abs(mats[0][8] - p.sum()) < 1e-10 * p.size and abs(mats[0][9] - p.var()) < 1e-9
+
+
+def _lonely_rank(q):
+    """child process: rank 0 of a 2-rank communicator issues a collective its peer never joins"""
+    sys.path.insert(0, ROOT)
+    os.environ["NUK_COMM_TIMEOUT_MS"] = "500"
+    import numericals_b200 as nu
+    from numericals_b200 import _lib
+    from numericals_b200.sharded import Communicator
+    import time
+    lib = _lib.lib()
+    comms = Communicator.init_all(2)
+    nu.require_device(0)
+    a = nu.asarray(np.arange(1024, dtype=np.float64))
+    t0 = time.time()
+    _lib.check(lib.nuk_comm_allreduce(comms[0].handle, 0, a.dtype_code, 1024, C.c_void_p(a.ptr), C.c_void_p(a.ptr), None))
+    lib.nuk_device_sync()                       # returns: the kernel gives up after the timeout, it does not hang
+    waited = time.time() - t0
+    st = lib.nuk_comm_status(comms[0].handle)
+    st2 = lib.nuk_comm_allreduce(comms[0].handle, 0, a.dtype_code, 1024, C.c_void_p(a.ptr), C.c_void_p(a.ptr), None)
+    q.put((st, st2, waited, lib.nuk_last_error().decode()))
+
+
+def test_absent_peer_times_out_instead_of_hanging():
+    """A peer that never arrives must not leave a spinning kernel behind: after NUK_COMM_TIMEOUT_MS the kernels
+    give up, nuk_comm_status and every later collective return NUK_ERR_COMM (5)."""
+    if _ndev() < 2:
+        pytest.skip("needs two devices")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    p = ctx.Process(target=_lonely_rank, args=(q,))
+    p.start()
+    st, st2, waited, msg = q.get(timeout=120)
+    p.join(timeout=60)
+    assert st == 5 and st2 == 5, (st, st2, msg)
+    assert 0.4 <= waited < 30, waited
+    assert "did not arrive" in msg
