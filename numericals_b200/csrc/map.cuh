@@ -22,6 +22,7 @@
 // OUT may alias X and/or Y exactly: every thread reads the elements it is going to
 // overwrite before it writes them, and no thread reads another thread's elements.
 #pragma once
+#include <utility>
 #include "common.cuh"
 
 namespace nuk {
@@ -139,6 +140,11 @@ k_map_flat(size_t n, const typename F::In *x, const typename F::In *y, typename 
   // MODE 0 is only launched with all-vector operands: the scalar bookkeeping folds away at compile time (it was
   // a third of the ~33-instruction per-thread prologue, i.e. ~0.7 instructions per element of a 16-element thread)
   const int x_scalar = (MODE == 0) ? 0 : x_scalar_arg, y_scalar = (MODE == 0) ? 0 : y_scalar_arg;
+  // Programmatic dependent launch (launch_flat below): this grid may have been scheduled while its predecessor
+  // in the stream was still draining.  Let OUR successor be scheduled as early, then wait for the predecessor to
+  // complete (and its writes to be visible) before touching memory.  Both are no-ops for an ordinary launch.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   using In = typename F::In;
   using Out = typename F::Out;
   using P = PackOf<F>;
@@ -318,6 +324,8 @@ k_map_flat2(size_t n, int64_t ncols, const typename F::In *x, const typename F::
   const size_t nfull = npack / kTile;
   POut *op = reinterpret_cast<POut *>(out);
   const In xs = scalar_as<In>(xv), ys = scalar_as<In>(yv);
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // programmatic dependent launch, as k_map_flat
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   auto load = [&](const In *ptr, int kind, int64_t rs, In sv, size_t pk, int64_t r, int64_t c) -> PIn {
     PIn v;
@@ -599,6 +607,36 @@ struct MapProblem {
 int build_problem(MapProblem *p, int arity, int rank, const int64_t *dims, const int64_t *sx,
                   const int64_t *sy, const int64_t *so);
 
+// Launch of the flat kernel with programmatic stream serialization: back-to-back small maps (C1: 10^6 doubles, ~3 us
+// of work each) are separated by ~1.1 us of launch latency in stream order; with the attribute the next grid is
+// scheduled while this one drains and blocks in griddepcontrol.wait until this one has completed -- the same
+// ordering, without the bubble (profiles/c1_latency_r02.txt).  Option pdl = 0 turns it off.
+template <typename... KArgs, typename... Args>
+int launch_pdl(void (*kernel)(KArgs...), const char *name, size_t grid, cudaStream_t stream, Args &&...args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = opt(OPT_PDL) != 0 ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+  if (e != cudaSuccess) {
+    set_error(NUK_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e));
+    cudaGetLastError();
+    return NUK_ERR_CUDA;
+  }
+  return post_launch(name);
+}
+template <class F, int FU, int MODE>
+int launch_flat(size_t grid, cudaStream_t stream, size_t n, const typename F::In *x, const typename F::In *y,
+                typename F::Out *out, int xs, int ys, const Scalar64 &xv, const Scalar64 &yv, const F &f) {
+  return launch_pdl(k_map_flat<F, FU, MODE>, "k_map_flat", grid, stream, n, x, y, out, xs, ys, xv, yv, f);
+}
+
 template <class F> int launch_map(const MapProblem &p, F f = F()) {
   using In = typename F::In;
   using Out = typename F::Out;
@@ -635,16 +673,11 @@ template <class F> int launch_map(const MapProblem &p, F f = F()) {
         return NUK_ERR_INVALID;
       }
       if constexpr ((HasFast<F>::value && F::kArity == 2) || F::kArity == 1) {
-        if (xs || (binary && ys))
-          k_map_flat<F, FU, 1><<<(unsigned)(nfull + 1), kThreads, 0, p.stream>>>(n, x, y, out, xs ? 1 : 0, ys ? 1 : 0,
-                                                                            p.xv, p.yv, f);
-        else
-          k_map_flat<F, FU, 0><<<(unsigned)(nfull + 1), kThreads, 0, p.stream>>>(n, x, y, out, 0, 0, p.xv, p.yv, f);
+        if (xs || (binary && ys)) return launch_flat<F, FU, 1>(nfull + 1, p.stream, n, x, y, out, xs ? 1 : 0, ys ? 1 : 0, p.xv, p.yv, f);
+        return launch_flat<F, FU, 0>(nfull + 1, p.stream, n, x, y, out, 0, 0, p.xv, p.yv, f);
       } else {
-        k_map_flat<F, FU><<<(unsigned)(nfull + 1), kThreads, 0, p.stream>>>(n, x, y, out, xs ? 1 : 0,
-                                                                         ys ? 1 : 0, p.xv, p.yv, f);
+        return launch_flat<F, FU, 2>(nfull + 1, p.stream, n, x, y, out, xs ? 1 : 0, ys ? 1 : 0, p.xv, p.yv, f);
       }
-      return post_launch("k_map_flat");
     }
   }
   // ---- flat with broadcast operands: rank 2, OUT one contiguous block, inputs laid out like OUT / row vector /
@@ -667,9 +700,8 @@ template <class F> int launch_map(const MapProblem &p, F f = F()) {
       Scalar64 xv = p.xv, yv = p.yv;
       // a (0, 0)-strided operand that lives in device memory is a one-element array: kind 2 with stride 0
       const int xk2 = (xk == 3 && x != nullptr) ? 2 : xk, yk2 = (yk == 3 && binary && y != nullptr) ? 2 : yk;
-      k_map_flat2<F, FU><<<(unsigned)(nfull + 1), kThreads, 0, p.stream>>>(
-          n, ncols, x, y, out, xk2, yk2, xk2 == 2 ? p.sx[0] : 0, yk2 == 2 ? p.sy[0] : 0, xv, yv, f);
-      return post_launch("k_map_flat2");
+      return launch_pdl(k_map_flat2<F, FU>, "k_map_flat2", nfull + 1, p.stream, n, ncols, x, y, out, xk2, yk2,
+                        (int64_t)(xk2 == 2 ? p.sx[0] : 0), (int64_t)(yk2 == 2 ? p.sy[0] : 0), xv, yv, f);
     }
   }
   // ---- rows: rank >= 2, inner axis contiguous for out, inputs 1/0 along it

@@ -20,7 +20,7 @@ int main(int argc, char **argv) {
   SYM(nuk_init) SYM(nuk_malloc) SYM(nuk_memcpy_h2d) SYM(nuk_memcpy_d2h) SYM(nuk_stream_create) SYM(nuk_set_stream)
   SYM(nuk_stream_sync) SYM(nuk_event_create) SYM(nuk_event_record) SYM(nuk_event_sync) SYM(nuk_event_elapsed_ms)
   SYM(nuk_set_pointer_mode) SYM(nuk_graph_begin) SYM(nuk_graph_end) SYM(nuk_graph_launch) SYM(nuk_last_status)
-  SYM(nuk_last_error) SYM(BMAS_dadd) SYM(nuk_flush_l2)
+  SYM(nuk_last_error) SYM(BMAS_dadd) SYM(nuk_flush_l2) SYM(nuk_set_option)
   if (p_nuk_init(0) != 0) { fprintf(stderr, "%s\n", p_nuk_last_error()); return 1; }
   const long n = 1000000;
   std::vector<double> ones(n, 1.0), out(n, 0.0);
@@ -51,6 +51,9 @@ int main(int argc, char **argv) {
   batch("BMAS_dadd, NUK_PTR_AUTO", 2000);
   p_nuk_set_pointer_mode(NUK_PTR_DEVICE);
   batch("BMAS_dadd, NUK_PTR_DEVICE", 2000);
+  p_nuk_set_option("pdl", 0);
+  batch("  same, ordinary launches (pdl = 0)", 2000);
+  p_nuk_set_option("pdl", 1);
   // graph: 20 calls captured once, replayed
   call();
   p_nuk_graph_begin(s);
