@@ -35,10 +35,10 @@ namespace nuk {
 #define NUK_FAST_TRIG32 2   // 0 per-element branches, 1 pack-level split (slower: profiles/fast_split_ab_r01.txt), 2 per-warp vote + called rare path (profiles/ab_warp_r02.txt: sin 0.955 -> 0.979, cos 0.962 -> 0.999 of the measured HBM peak)
 #endif
 #ifndef NUK_FAST_HYP32
-#define NUK_FAST_HYP32 1    // sinh cosh asinh acosh atanh: +2..3 points with the split and no register cap
+#define NUK_FAST_HYP32 2    // sinh cosh: per-warp vote (profiles/ab_invtrig_r02.txt: sinh 0.783 pack split, 0.824 per-element branches, 0.859 warp vote)
 #endif
 #ifndef NUK_FAST_ATAN2F
-#define NUK_FAST_ATAN2F false   // measured slower with the split (profiles/fast_split_ab_r01.txt)
+#define NUK_FAST_ATAN2F 2   // 0 per-element branch (round 1: the pack split measured slower, profiles/fast_split_ab_r01.txt), 1 pack split, 2 per-warp vote
 #endif
 // measured on B200 (profiles/time_unroll_r01.txt, 2^28 elements): 4 packs per thread beat 1 by 15-30 % for
 // every unary below (tan 5.2 vs 4.2 TB/s, cosh 5.2 vs 4.0), 2 packs are best for the binary ones
@@ -71,14 +71,20 @@ namespace nuk {
 #define NUK_TANH32_UNROLL 4
 #endif
 #ifndef NUK_TAN32_UNROLL
-#define NUK_TAN32_UNROLL NUK_F32_UNROLL
+#define NUK_TAN32_UNROLL 8
 #endif
 NUK_F32_UNARY_FAST(SinF, sin_f32, NUK_TRIG32_UNROLL, NUK_TRIG32_MINB, NUK_FAST_TRIG32) NUK_F32_UNARY_FAST(CosF, cos_f32, NUK_TRIG32_UNROLL, NUK_TRIG32_MINB, NUK_FAST_TRIG32)
 NUK_F32_UNARY_FAST(TanhF, tanh_f32, NUK_TANH32_UNROLL, NUK_TANH32_MINB, NUK_FAST_TANH32)
 NUK_F32_UNARY(LogF, log_f32)
 NUK_F32_UNARY_U(ExpF, exp_f32, 2)   // 5.9 TB/s with 2 packs per thread vs 5.2 with 4 (profiles/membench_r01.txt)
-NUK_F32_UNARY_FAST(TanF, tan_f32, NUK_TAN32_UNROLL, 0, NUK_FAST_TRIG32) NUK_F32_VIA_F64(AsinF, asin_f32) NUK_F32_VIA_F64(AcosF, acos_f32)
-NUK_F32_VIA_F64(AtanF, atan_f32) NUK_F32_UNARY_FAST(SinhF, sinh_f32, NUK_F32_UNROLL, 0, NUK_FAST_HYP32) NUK_F32_UNARY_FAST(CoshF, cosh_f32, NUK_F32_UNROLL, 0, NUK_FAST_HYP32)
+#ifndef NUK_FAST_ATAN32
+#define NUK_FAST_ATAN32 2   // asin acos atan: branch-free main path, per-warp vote, called rare path
+#endif
+#ifndef NUK_ATAN32_UNROLL
+#define NUK_ATAN32_UNROLL 8 // profiles/ab_invtrig_r02.txt: asin 1.00 -> 1.06, acos 0.94 -> 0.99, atan 0.93 -> 0.98 of the measured peak with 8 packs per thread
+#endif
+NUK_F32_UNARY_FAST(TanF, tan_f32, NUK_TAN32_UNROLL, 0, NUK_FAST_TRIG32) NUK_F32_UNARY_FAST(AsinF, asin_f32, NUK_ATAN32_UNROLL, 0, NUK_FAST_ATAN32) NUK_F32_UNARY_FAST(AcosF, acos_f32, NUK_ATAN32_UNROLL, 0, NUK_FAST_ATAN32)
+NUK_F32_UNARY_FAST(AtanF, atan_f32, NUK_ATAN32_UNROLL, 0, NUK_FAST_ATAN32) NUK_F32_UNARY_FAST(SinhF, sinh_f32, NUK_F32_UNROLL, 0, NUK_FAST_HYP32) NUK_F32_UNARY_FAST(CoshF, cosh_f32, NUK_F32_UNROLL, 0, NUK_FAST_HYP32)
 // asinh / acosh / atanh: double arithmetic on the 640 bytes of single-float pow tables (nukmath_tab.cuh)
 #ifndef NUK_HYPINV32_MINB
 #define NUK_HYPINV32_MINB 0
@@ -101,8 +107,9 @@ struct Atan2F {
   using In = float; using Out = float;
   static constexpr int kArity = 2;
   static constexpr int kMapUnroll = 2;
-  static constexpr int kMapMinBlocks = NUK_FAST_ATAN2F ? NUK_F32_MINB : 0;
-  static constexpr bool kHasFast = NUK_FAST_ATAN2F;
+  static constexpr int kMapMinBlocks = 0;
+  static constexpr bool kHasFast = NUK_FAST_ATAN2F == 1;
+  static constexpr bool kWarpSplit = NUK_FAST_ATAN2F == 2;
   NUK_D float operator()(float a, float b) const { return nukmath::atan2_f32(a, b); }
   NUK_D float fast(float a, float b, bool &slow) const { return nukmath::atan2_f32_fast(a, b, slow); }
 };

@@ -148,6 +148,35 @@ static int sweep32(const Fn32 &fn, uint64_t lo_bits, uint64_t hi_bits) {
   return (w < 1.0 && sd <= 1) ? 0 : 1;
 }
 
+// "fast32": the branch-free main paths (map.cuh:HasFast / kWarpSplit) against the complete functions, all 2^32 bit
+// patterns: wherever fast() does not raise `slow` its result must be the complete function's, bit for bit.
+typedef float (*f32_fast_fn)(float, bool &);
+struct Fast32 { const char *name; f32_fn full; f32_fast_fn fast; };
+static const Fast32 kFast32[] = {
+  {"log", nukmath::log_f32, nukmath::log_f32_fast},   {"sin", nukmath::sin_f32, nukmath::sin_f32_fast},
+  {"cos", nukmath::cos_f32, nukmath::cos_f32_fast},   {"tan", nukmath::tan_f32, nukmath::tan_f32_fast},
+  {"tanh", nukmath::tanh_f32, nukmath::tanh_f32_fast}, {"sinh", nukmath::sinh_f32, nukmath::sinh_f32_fast},
+  {"cosh", nukmath::cosh_f32, nukmath::cosh_f32_fast}, {"atan", nukmath::atan_f32, nukmath::atan_f32_fast},
+  {"asin", nukmath::asin_f32, nukmath::asin_f32_fast}, {"acos", nukmath::acos_f32, nukmath::acos_f32_fast},
+};
+static int fastcheck32(const Fast32 &fn) {
+  uint64_t bad = 0, slow_n = 0; uint32_t bad_at = 0;
+#pragma omp parallel for schedule(static) reduction(+ : bad, slow_n)
+  for (uint64_t b = 0; b < (1ull << 32); ++b) {
+    const uint32_t u = (uint32_t)b;
+    float x; memcpy(&x, &u, 4);
+    bool slow = false;
+    const float f = fn.fast(x, slow);
+    if (slow) { ++slow_n; continue; }
+    const float g = fn.full(x);
+    if (memcmp(&f, &g, 4) != 0 && !(f != f && g != g)) { ++bad; bad_at = u; }
+  }
+  float bx; memcpy(&bx, &bad_at, 4);
+  printf("{\"fn\": \"%s\", \"type\": \"fast32\", \"inputs\": 4294967296, \"flagged_slow\": %llu, \"fast_differs_from_full\": %llu, \"at\": \"%a\"}\n",
+         fn.name, (unsigned long long)slow_n, (unsigned long long)bad, bx);
+  return bad ? 1 : 0;
+}
+
 #ifdef NUK_HAVE_F64
 #include "ulp_sweep_f64.inc"
 #endif
@@ -165,6 +194,10 @@ int main(int argc, char **argv) {
     if (argc > 4) { lo = strtoull(argv[3], 0, 0); hi = strtoull(argv[4], 0, 0); }
     for (const Fn32 &f : kFn32)
       if (which == "all" || which == f.name) rc |= sweep32(f, lo, hi);
+  }
+  else if (type == "fast32") {
+    for (const Fast32 &f : kFast32)
+      if (which == "all" || which == f.name) rc |= fastcheck32(f);
   }
 #ifdef NUK_HAVE_F64
   else rc = sweep64_main(which, argc, argv);
