@@ -92,17 +92,24 @@ NUK_F32_UNARY_FAST(AtanF, atan_f32, NUK_ATAN32_UNROLL, 0, NUK_FAST_ATAN32) NUK_F
 #ifndef NUK_HYPINV32_UNROLL
 #define NUK_HYPINV32_UNROLL 2
 #endif
-#define NUK_F32_UNARY_TAB(Name, FN)                     \
+#define NUK_F32_UNARY_TAB(Name, FN, UNR, ON)            \
   struct Name : TabPowF {                               \
     using In = float; using Out = float;                \
     static constexpr int kArity = 1;                    \
-    static constexpr int kMapUnroll = NUK_HYPINV32_UNROLL; \
+    static constexpr int kMapUnroll = UNR;              \
     static constexpr int kMapMinBlocks = NUK_HYPINV32_MINB; \
-    static constexpr bool kHasFast = true;              \
+    static constexpr bool kHasFast = (ON) == 1;         \
+    static constexpr bool kWarpSplit = (ON) == 2;       \
     NUK_D float operator()(float a) const { return nukmath::FN(a, tab); } \
     NUK_D float fast(float a, bool &slow) const { return nukmath::FN##_fast(a, tab, slow); } \
   };
-NUK_F32_UNARY_TAB(AsinhF, asinh_f32) NUK_F32_UNARY_TAB(AcoshF, acosh_f32) NUK_F32_UNARY_TAB(AtanhF, atanh_f32)
+// asinh on |x| <= 1 and acosh on (1, 3] are single-float polynomials (nukmath_f32.cuh:asinh_small_f32 / acosh_near_f32:
+// ~20 / ~28 instructions per element, HBM-bound); a warp holding anything else calls the complete double-table function
+#ifndef NUK_ASINH32_UNROLL
+#define NUK_ASINH32_UNROLL 8
+#endif
+NUK_F32_UNARY_TAB(AsinhF, asinh_f32, NUK_ASINH32_UNROLL, 2) NUK_F32_UNARY_TAB(AcoshF, acosh_f32, NUK_ASINH32_UNROLL, 2)
+NUK_F32_UNARY_TAB(AtanhF, atanh_f32, NUK_HYPINV32_UNROLL, 1)
 struct Atan2F {
   using In = float; using Out = float;
   static constexpr int kArity = 2;

@@ -152,7 +152,16 @@ static int sweep32(const Fn32 &fn, uint64_t lo_bits, uint64_t hi_bits) {
 // patterns: wherever fast() does not raise `slow` its result must be the complete function's, bit for bit.
 typedef float (*f32_fast_fn)(float, bool &);
 struct Fast32 { const char *name; f32_fn full; f32_fast_fn fast; };
+#ifdef NUK_HAVE_F64
+static float asinh_f32_fast_h(float x, bool &s) { return nukmath::asinh_f32_fast(x, nukmath::TabRef{nukmath::kTabImageF}, s); }
+static float acosh_f32_fast_h(float x, bool &s) { return nukmath::acosh_f32_fast(x, nukmath::TabRef{nukmath::kTabImageF}, s); }
+static float atanh_f32_fast_h(float x, bool &s) { return nukmath::atanh_f32_fast(x, nukmath::TabRef{nukmath::kTabImageF}, s); }
+#endif
 static const Fast32 kFast32[] = {
+#ifdef NUK_HAVE_F64
+  {"asinh", nukmath::asinh_f32, asinh_f32_fast_h}, {"acosh", nukmath::acosh_f32, acosh_f32_fast_h},
+  {"atanh", nukmath::atanh_f32, atanh_f32_fast_h},
+#endif
   {"log", nukmath::log_f32, nukmath::log_f32_fast},   {"sin", nukmath::sin_f32, nukmath::sin_f32_fast},
   {"cos", nukmath::cos_f32, nukmath::cos_f32_fast},   {"tan", nukmath::tan_f32, nukmath::tan_f32_fast},
   {"tanh", nukmath::tanh_f32, nukmath::tanh_f32_fast}, {"sinh", nukmath::sinh_f32, nukmath::sinh_f32_fast},

@@ -179,16 +179,18 @@ def main():
                 (r0, r1, float(mp.log(el, 2))))
         f.write("// e^r - 1 - r = r^2 E(r), |r| <= %.6g, absolute error 2^%.2f\n" % (s32, float(mp.log(ee, 2))))
         f.write("#define NM_TF_OFF 0x%08xu\n" % OFF32)
-        f.write("// kTabPF: L0..L4, E0..E2, ln2, 32/ln2, -ln2/32, 1.5*2^52\n")
-        consts = [float(c) for c in list(L32) + list(E32)] + [rd(mp.log(2)), rd(32 / mp.log(2)), rd(-mp.log(2) / 32), 1.5 * 2.0 ** 52]
+        f.write("// kTabPF: L0..L4, E0..E2, ln2, 32/ln2, -ln2/32, 1.5*2^52, ln2 * 2^-20\n")
+        consts = [float(c) for c in list(L32) + list(E32)] + [rd(mp.log(2)), rd(32 / mp.log(2)), rd(-mp.log(2) / 32), 1.5 * 2.0 ** 52, rd(mp.log(2)) * 2.0 ** -20]
         f.write("#define NM_TABF_POLY { %s }\n" % ", ".join(c.hex() for c in consts))
-        f.write("// image (uint64 words): [0,32) log c; [32,64) bits(2^(j/32)) - (j << 47); [64,80) 1/c as 32 floats\n")
-        words = [hexd(v) for v in logc] + ["0x%016xull" % v for v in expt]
-        for k in range(0, 32, 2):
-            words.append("0x%016xull" % (f2u32(invc[k]) | (f2u32(invc[k + 1]) << 32)))
-        f.write("#define NM_TABF_WORDS 80\n#define NM_TABF_IMAGE { \\\n")
-        for k in range(0, 80, 4):
-            f.write("  " + ", ".join(words[k:k + 4]) + (", \\\n" if k + 4 < 80 else " }\n"))
+        f.write("// image (uint64 words): [0,64) {1/c, log c} pairs of doubles (one 16-byte read per element, no widening of a\n")
+        f.write("// single-float 1/c); [64,96) bits(2^(j/32)) - (j << 47)\n")
+        words = []
+        for k in range(32):
+            words += [hexd(invc[k]), hexd(logc[k])]
+        words += ["0x%016xull" % v for v in expt]
+        f.write("#define NM_TABF_WORDS 96\n#define NM_TABF_IMAGE { \\\n")
+        for k in range(0, 96, 4):
+            f.write("  " + ", ".join(words[k:k + 4]) + (", \\\n" if k + 4 < 96 else " }\n"))
     print("pow32: r in [%g, %g], log poly 2^%.2f, exp poly 2^%.2f" % (r0, r1, float(mp.log(el, 2)), float(mp.log(ee, 2))))
     print("wrote", os.path.normpath(out))
     print("log: r in [%g, %g], poly err 2^%.2f; exp: poly err 2^%.2f" %

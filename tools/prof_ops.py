@@ -21,12 +21,15 @@ rng = np.random.default_rng(0)
 bufs = {}
 for p, dt in (("s", np.float32), ("d", np.float64)):
     bufs[p] = [nu.asarray((rng.random(n) * 0.9 + 0.05).astype(dt)) for _ in range(2)] + [nu.empty((n,), dt)]
+    bufs[p + "+1"] = nu.asarray((rng.random(n) * 0.9 + 1.05).astype(dt))     # acosh: U[1.05, 1.95) as tools/sweep.py
 L, P = C.c_long, C.c_void_p
 BIN = {"pow", "atan2", "add", "sub", "mul", "div", "max", "min"}
 for _ in range(reps):
     for s in syms:
         p = s[0]
         x, y, o = bufs[p]
+        if s[1:] == "acosh":
+            x = bufs[p + "+1"]
         if s[1:] in BIN:
             _lib.bmas(s)(L(n), P(x.ptr), L(1), P(y.ptr), L(1), P(o.ptr), L(1))
         else:
