@@ -96,6 +96,16 @@ template <class F> struct WarpSplit<F, std::void_t<decltype(F::kHasFast)>> { sta
 #else
 template <class F> struct WarpSplit<F, std::void_t<decltype(F::kWarpSplit)>> { static constexpr bool value = F::kWarpSplit; };
 #endif
+// kFastBatch: the pack-level split over the WHOLE thread tile: fast() for all UNROLL x E elements first, one test of
+// the collected flags, flagged elements re-done, then the stores.  The table-driven double functors wait on two
+// dependent shared-memory reads per element (ncu: 7-10 warps per issue stalled on the short scoreboard, issue slots
+// 40-58 % busy for sinh / cosh); with every element of the tile in one straight-line block the compiler overlaps
+// those reads across elements instead of across two.
+template <class F, class = void> struct FastBatch { static constexpr bool value = false; };
+template <class F> struct FastBatch<F, std::void_t<decltype(F::kFastBatch)>> { static constexpr bool value = F::kFastBatch; };
+// kBatchCall: the re-do of a flagged element CALLS the complete function (one copy per kernel) instead of inlining it
+template <class F, class = void> struct BatchCall { static constexpr bool value = false; };
+template <class F> struct BatchCall<F, std::void_t<decltype(F::kBatchCall)>> { static constexpr bool value = F::kBatchCall; };
 template <class F> __device__ __noinline__ typename F::Out apply_called(F f, typename F::In a, typename F::In b) {
   if constexpr (F::kArity == 2) return f(a, b);
   else return f(a);
@@ -177,6 +187,33 @@ k_map_flat(size_t n, const typename F::In *x, const typename F::In *y, typename 
       for (int u = 0; u < UNROLL; ++u) b[u] = ld_stream(yp + base + (size_t)u * kThreads);
     }
     stage_tables(f);   // after the operand loads are in flight: the table copy hides under their latency
+    if constexpr (FastBatch<F>::value) {
+      POut r[UNROLL];
+      uint32_t flags = 0;
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          bool s1 = false;
+          r[u].v[e] = apply_fast(f, a[u].v[e], F::kArity == 2 ? b[u].v[e] : In(), s1);
+          flags |= (uint32_t)s1 << (u * E + e);
+        }
+      }
+      if (flags) {
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+#pragma unroll
+          for (int e = 0; e < E; ++e)
+            if ((flags >> (u * E + e)) & 1u) {
+              if constexpr (BatchCall<F>::value) r[u].v[e] = apply_called(f, a[u].v[e], F::kArity == 2 ? b[u].v[e] : In());
+              else r[u].v[e] = apply_rare(f, a[u].v[e], F::kArity == 2 ? b[u].v[e] : In());
+            }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) st_stream(op + base + (size_t)u * kThreads, r[u]);
+      return;
+    }
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
       POut r;

@@ -26,9 +26,10 @@ template <const uint64_t *IMAGE, int BYTES, int W0, int W1> struct TabStageOf {
   }
 };
 template <int W0, int W1> using TabStage = TabStageOf<nukmath::kTabImage, nukmath::kTabBytes, W0, W1>;
-using TabAll = TabStage<0, NM_TAB_WORDS>;
+using TabAll = TabStage<0, 640>;
 using TabLog = TabStage<0, 384>;
-using TabExp = TabStage<384, NM_TAB_WORDS>;
+using TabExp = TabStage<384, 640>;
+using TabExp32 = TabStage<640, NM_TAB_WORDS>;   // the 32-entry exp table of sinh / cosh
 using TabPowF = TabStageOf<nukmath::kTabImageF, nukmath::kTabFBytes, 0, NM_TABF_WORDS>;
 
 }  // namespace nuk

@@ -22,13 +22,14 @@ namespace nuk {
 #ifndef NUK_F64_UNROLL
 #define NUK_F64_UNROLL 2
 #endif
-#define NUK_F64_UNARY_FAST(Name, FN, MINB, ON)           \
+#define NUK_F64_UNARY_FAST(Name, FN, MINB, ON, UNR, BATCH) \
   struct Name {                                         \
     using In = double; using Out = double;              \
     static constexpr int kArity = 1;                    \
-    static constexpr int kMapUnroll = NUK_F64_UNROLL;   \
+    static constexpr int kMapUnroll = UNR;              \
     static constexpr int kMapMinBlocks = MINB;          \
     static constexpr bool kHasFast = ON;                \
+    static constexpr bool kFastBatch = (ON) && (BATCH); /* whole-tile batch (map.cuh:kFastBatch) */ \
     NUK_D double operator()(double a) const { return nukmath::FN(a); } \
     NUK_D double fast(double a, bool &slow) const { return nukmath::FN##_fast(a, slow); } \
   };
@@ -47,11 +48,26 @@ namespace nuk {
 #ifndef NUK_TRIG_MINB
 #define NUK_TRIG_MINB 4
 #endif
+#ifndef NUK_SINCOS64_UNROLL
+#define NUK_SINCOS64_UNROLL NUK_F64_UNROLL
+#endif
+#ifndef NUK_ATAN64_UNROLL
+#define NUK_ATAN64_UNROLL NUK_F64_UNROLL
+#endif
+#ifndef NUK_ATAN64_BATCH
+#define NUK_ATAN64_BATCH 0
+#endif
+#ifndef NUK_ATAN64_MINB
+#define NUK_ATAN64_MINB NUK_TRIG_MINB
+#endif
+#ifndef NUK_ASIN64_MINB
+#define NUK_ASIN64_MINB 0
+#endif
 // cos capped at 32 registers: 74 -> 86 % (profiles/minblocks_sweep_r01.txt)
-NUK_F64_UNARY_FAST(SinD, sin_f64, 0, false) NUK_F64_UNARY_FAST(CosD, cos_f64, 8, false)
-NUK_F64_UNARY_FAST(TanD, tan_f64, 5, NUK_FAST_TRIG64)
-NUK_F64_UNARY_FAST(AsinD, asin_f64, 0, NUK_FAST_INV64) NUK_F64_UNARY_FAST(AcosD, acos_f64, 0, NUK_FAST_INV64)
-NUK_F64_UNARY_FAST(AtanD, atan_f64, NUK_TRIG_MINB, NUK_FAST_INV64)
+NUK_F64_UNARY_FAST(SinD, sin_f64, 0, false, NUK_SINCOS64_UNROLL, 0) NUK_F64_UNARY_FAST(CosD, cos_f64, 8, false, NUK_SINCOS64_UNROLL, 0)
+NUK_F64_UNARY_FAST(TanD, tan_f64, 5, NUK_FAST_TRIG64, NUK_F64_UNROLL, 0)
+NUK_F64_UNARY_FAST(AsinD, asin_f64, NUK_ASIN64_MINB, NUK_FAST_INV64, NUK_F64_UNROLL, 0) NUK_F64_UNARY_FAST(AcosD, acos_f64, NUK_ASIN64_MINB, NUK_FAST_INV64, NUK_F64_UNROLL, 0)
+NUK_F64_UNARY_FAST(AtanD, atan_f64, NUK_ATAN64_MINB, NUK_FAST_INV64, NUK_ATAN64_UNROLL, NUK_ATAN64_BATCH)
 struct Atan2D {
   using In = double; using Out = double;
   static constexpr int kArity = 2;
@@ -119,10 +135,52 @@ NUK_F64_TAB_UNARY(ExpD, exp_f64, TabExp, 6) NUK_F64_TAB_UNARY(LogD, log_f64, Tab
     NUK_D double operator()(double a) const { return nukmath::FN(a, tab); } \
     NUK_D double fast(double a, bool &slow) const { return nukmath::FN##_fast(a, tab, slow); } \
   };
-NUK_F64_TAB_UNARY_FAST2(AsinhD, asinh_f64, TabLog, NUK_IHYP_MINB, NUK_FAST_IHYP64)
-NUK_F64_TAB_UNARY_FAST2(AcoshD, acosh_f64, TabLog, NUK_IHYP_MINB, NUK_FAST_IHYP64)
+// asinh on |x| <= 1 and acosh on (1, 3] are polynomial main paths (nukmath_tab.cuh:asinh_small_f64 / acosh_near_f64);
+// the complete functions (logarithm path) are CALLED for a warp that holds anything else (map.cuh:kWarpSplit)
+#ifndef NUK_IHYP64_SPLIT
+#define NUK_IHYP64_SPLIT 2   // (profiles/ab_f64_r02.txt: asinh 1.05 with the vote, 0.83 with the batch) 1 pack split (complete function inlined per flagged element), 2 per-warp vote + call, 3 whole-tile batch + call (the 22 coefficients are fetched once per tile, not once per element)
+#endif
+#ifndef NUK_IHYP64_UNROLL
+#define NUK_IHYP64_UNROLL 4
+#endif
+#define NUK_F64_TAB_UNARY_REGION(Name, FN, Stage)       \
+  struct Name : Stage {                                 \
+    using In = double; using Out = double;              \
+    static constexpr int kArity = 1;                    \
+    static constexpr int kMapUnroll = NUK_IHYP64_UNROLL; \
+    static constexpr int kMapMinBlocks = 0;             \
+    static constexpr bool kHasFast = NUK_IHYP64_SPLIT == 1 || NUK_IHYP64_SPLIT == 3; \
+    static constexpr bool kWarpSplit = NUK_IHYP64_SPLIT == 2; \
+    static constexpr bool kFastBatch = NUK_IHYP64_SPLIT == 3; \
+    static constexpr bool kBatchCall = true;            \
+    NUK_D double operator()(double a) const { return nukmath::FN(a, tab); } \
+    NUK_D double fast(double a, bool &slow) const { return nukmath::FN##_fast(a, tab, slow); } \
+  };
+NUK_F64_TAB_UNARY_REGION(AsinhD, asinh_f64, TabLog) NUK_F64_TAB_UNARY_REGION(AcoshD, acosh_f64, TabLog)
 NUK_F64_TAB_UNARY_FAST2(AtanhD, atanh_f64, TabLog, NUK_IHYP_MINB, NUK_FAST_IHYP64)
-NUK_F64_TAB_UNARY(SinhD, sinh_f64, TabExp, 6) NUK_F64_TAB_UNARY_FAST(CoshD, cosh_f64, TabExp, 5)
+// sinh / cosh: ~50-64 instructions per element and two per-lane indexed table reads each (the 32-entry table: 4
+// shared-memory wavefronts per read)
+#ifndef NUK_HYP64_BATCH
+#define NUK_HYP64_BATCH 0   // profiles/ab_f64_r02.txt: the whole-tile batch is slower here (0.63 vs 0.73 of the measured peak)
+#endif
+#ifndef NUK_HYP64_MINB
+#define NUK_HYP64_MINB 0
+#endif
+#ifndef NUK_HYP64_UNROLL
+#define NUK_HYP64_UNROLL 4
+#endif
+#define NUK_F64_TAB_UNARY_BATCH(Name, FN, Stage)        \
+  struct Name : Stage {                                 \
+    using In = double; using Out = double;              \
+    static constexpr int kArity = 1;                    \
+    static constexpr int kMapUnroll = NUK_HYP64_UNROLL; \
+    static constexpr int kMapMinBlocks = NUK_HYP64_MINB; \
+    static constexpr bool kHasFast = true;              \
+    static constexpr bool kFastBatch = NUK_HYP64_BATCH; \
+    NUK_D double operator()(double a) const { return nukmath::FN(a, tab); } \
+    NUK_D double fast(double a, bool &slow) const { return nukmath::FN##_fast(a, tab, slow); } \
+  };
+NUK_F64_TAB_UNARY_BATCH(SinhD, sinh_f64, TabExp32) NUK_F64_TAB_UNARY_BATCH(CoshD, cosh_f64, TabExp32)
 struct TanhD : TabExp {
   using In = double; using Out = double;
   static constexpr int kArity = 1;

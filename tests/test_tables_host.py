@@ -36,7 +36,7 @@ def test_generated_file_is_current(tmp_path):
 
 def test_double_tables_have_the_properties_the_kernels_use():
     w = words("NM_TAB_IMAGE")
-    assert len(w) == 640
+    assert len(w) == 704
     off = int(re.search(r"#define NM_TL_OFF 0x([0-9a-f]+)ull", open(INC).read()).group(1), 16)
     for i in range(128):
         invc, logc, tail = Fraction(u2d(w[2 * i])), u2d(w[2 * i + 1]), u2d(w[256 + i])
@@ -54,6 +54,17 @@ def test_double_tables_have_the_properties_the_kernels_use():
         tail, sb = u2d(w[384 + 2 * j]), w[384 + 2 * j + 1]
         H = u2d((sb + (j << 45)) & 0xFFFFFFFFFFFFFFFF)
         v = mp.mpf(2) ** (mp.mpf(j) / 128)
+        assert 1.0 <= H < 2.0 and abs(v - mp.mpf(H)) <= mp.mpf(2) ** -53, j
+        assert abs((v - mp.mpf(H)) / mp.mpf(H) - tail) < mp.mpf(2) ** -105, j
+
+
+def test_exp32_table():
+    """the 32-entry table of sinh / cosh: 2^(j/32) = H (1 + tail) to 2^-105"""
+    w = words("NM_TAB_IMAGE")
+    for j in range(32):
+        tail, sb = u2d(w[640 + 2 * j]), w[640 + 2 * j + 1]
+        H = u2d((sb + (j << 47)) & 0xFFFFFFFFFFFFFFFF)
+        v = mp.mpf(2) ** (mp.mpf(j) / 32)
         assert 1.0 <= H < 2.0 and abs(v - mp.mpf(H)) <= mp.mpf(2) ** -53, j
         assert abs((v - mp.mpf(H)) / mp.mpf(H) - tail) < mp.mpf(2) ** -105, j
 

@@ -72,13 +72,15 @@ def log_table():
     return rows, float(rmin), float(rmax)
 
 
-def exp_table():
+def exp_table(n=N, shift=45):
+    """2^(j/n) = H_j (1 + tail_j); the entry holds bits(H_j) - (j << shift) so that adding ki << shift (ki = n k + j)
+    puts k into the exponent field (shift = 52 - log2 n)"""
     rows = []
-    for j in range(N):
-        v = mp.mpf(2) ** (mp.mpf(j) / N)
+    for j in range(n):
+        v = mp.mpf(2) ** (mp.mpf(j) / n)
         H = rd(v)
         tail = rd((v - mp.mpf(H)) / mp.mpf(H))
-        rows.append((tail, (d2u(H) - (j << 45)) & 0xFFFFFFFFFFFFFFFF))
+        rows.append((tail, (d2u(H) - (j << shift)) & 0xFFFFFFFFFFFFFFFF))
     return rows
 
 
@@ -137,6 +139,14 @@ def main():
     we = lambda t: t * t
     se = float(mp.log(2) / 256) * 1.002
     C, ec = remez.fit(ge, we, -se, se, 4, None, "f64", grid=600)
+    # sinh / cosh: a 32-entry table (512 bytes: at most 4 rows of shared memory, so a per-lane indexed 16-byte read
+    # costs 4 wavefronts instead of the ~8 of the 128-entry one) and two more coefficients:
+    # e^r = 1 + r + r^2 (D0 + ... + D5 r^5) on |r| <= ln2/64 (1 + 2^-10); absolute error
+    et32 = exp_table(32, 47)
+    s32e = float(mp.log(2) / 64) * 1.002
+    Dc, ed = remez.fit(ge, we, -s32e, s32e, 6, None, "f64", grid=600)
+    l2n32_hi = mp.nint(mp.log(2) / 32 * 2 ** 42) / 2 ** 42   # ln2/32 to 37 bits: ki*hi exact for |ki| < 2^16
+    l2n32_lo = rd(mp.log(2) / 32 - l2n32_hi)
     ln2 = mp.log(2)
     ln2hi = mp.nint(ln2 * 2 ** 42) / 2 ** 42                 # 42 bits: k*LN2HI exact for |k| < 2^11
     ln2lo = rd(ln2 - ln2hi)
@@ -153,20 +163,27 @@ def main():
         f.write("#define NM_TE_INVLN2N %s\n" % rd(N / ln2).hex())
         f.write("#define NM_TE_LN2HIN %s\n" % float(l2n_hi).hex())
         f.write("#define NM_TE_LN2LON %s\n" % float(l2n_lo).hex())
+        f.write("// 32-entry exp (sinh / cosh): |r| <= %.6g, max absolute error 2^%.2f\n" % (s32e, float(mp.log(ed, 2))))
+        f.write("#define NM_TE32_INVLN2N %s\n" % rd(32 / ln2).hex())
+        f.write("#define NM_TE32_LN2HIN %s\n" % float(l2n32_hi).hex())
+        f.write("#define NM_TE32_LN2LON %s\n" % float(l2n32_lo).hex())
+        f.write("#define NM_TAB_POLY32 { %s }\n" % ", ".join(float(c).hex() for c in Dc))
         f.write("// kTabPoly: -2*B0..-2*B5 (log1p; the kernel multiplies by -r^2/2), C0..C3 (exp)\n")
         f.write("#define NM_TAB_POLY { %s }\n" % ", ".join(float(c).hex() for c in [-2 * b for b in B] + list(C)))
         f.write("// image layout (uint64 words): [0,256) log {invc, logc} pairs; [256,384) logctail;\n")
-        f.write("// [384,640) exp {tail, bits(H) - (j << 45)} pairs\n")
-        f.write("#define NM_TAB_WORDS 640\n#define NM_TAB_IMAGE { \\\n")
+        f.write("// [384,640) exp {tail, bits(H) - (j << 45)} pairs; [640,704) 32-entry exp {tail, bits(H) - (j << 47)} pairs\n")
+        f.write("#define NM_TAB_WORDS 704\n#define NM_TAB_IMAGE { \\\n")
         words = []
         for invc, logc, _ in lt:
             words += [hexd(invc), hexd(logc)]
         words += [hexd(t) for _, _, t in lt]
         for tail, sb in et:
             words += [hexd(tail), "0x%016xull" % sb]
-        assert len(words) == 640
-        for k in range(0, 640, 4):
-            f.write("  " + ", ".join(words[k:k + 4]) + (", \\\n" if k + 4 < 640 else " }\n"))
+        for tail, sb in et32:
+            words += [hexd(tail), "0x%016xull" % sb]
+        assert len(words) == 704
+        for k in range(0, 704, 4):
+            f.write("  " + ", ".join(words[k:k + 4]) + (", \\\n" if k + 4 < 704 else " }\n"))
     # ---- single-float pow
     invc, logc, expt, r0, r1 = pow32_tables()
     g32 = lambda t: (mp.log1p(t) - t) / t ** 2 if t != 0 else -mp.mpf(1) / 2
