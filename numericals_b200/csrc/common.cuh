@@ -49,7 +49,7 @@ struct ApiRange {
 // NUK_* knobs: lock-free reads on the launch path (nuk_set_option / the environment write them)
 enum Opt {
   OPT_GRID_MULT = 0, OPT_REDUCE_GRID_MULT, OPT_STAGE_MB, OPT_STAGE_SLOTS, OPT_COL_SPLIT_ROWS, OPT_SEQ_COLS,
-  OPT_STAGE_THREADS, OPT_ROWS_CTAS_PER_SM, OPT_STAGE_BOUNCE, OPT_ROWS_RPC, OPT_PDL, OPT_COUNT
+  OPT_STAGE_THREADS, OPT_ROWS_CTAS_PER_SM, OPT_STAGE_BOUNCE, OPT_ROWS_RPC, OPT_PDL, OPT_STAGE_NT, OPT_COUNT
 };
 long opt(Opt o);
 

@@ -138,7 +138,7 @@ int post_launch(const char *kernel) {
 // reference calls the C layer from concurrent lparallel workers, src/transcendental/lparallel.lisp:70-96).
 static const char *const kOptNames[OPT_COUNT] = {"grid_mult", "reduce_grid_mult", "stage_mb", "stage_slots",
                                                  "col_split_rows", "seq_cols", "stage_threads", "rows_ctas_per_sm",
-                                                 "stage_bounce", "rows_rpc", "pdl"};
+                                                 "stage_bounce", "rows_rpc", "pdl", "stage_nt"};
 static std::atomic<long> g_opts[OPT_COUNT];
 static std::once_flag g_opts_once;
 static void init_opts() {
@@ -151,6 +151,7 @@ static void init_opts() {
   g_opts[OPT_STAGE_THREADS] = 0;      // host mover threads for pageable / strided host operands (0 = auto)
   g_opts[OPT_STAGE_BOUNCE] = 1;       // 0: hand pageable |inc| == 1 operands to the driver's own pageable copy (A/B only)
   g_opts[OPT_PDL] = 1;                // flat maps launch with programmatic stream serialization (map.cuh:launch_flat)
+  g_opts[OPT_STAGE_NT] = 1;           // 1: non-temporal stores INTO the page-locked ring too (0: cached stores, for rings small enough to stay in L3)
   g_opts[OPT_ROWS_RPC] = 0;           // rows kernel: rows per CTA (0 = built-in rule)
   g_opts[OPT_ROWS_CTAS_PER_SM] = 0;   // rows kernel: CTAs per SM the row grouping aims for (0 = built-in rule)
   for (int i = 0; i < OPT_COUNT; ++i) {

@@ -148,9 +148,10 @@ static void scatter(const void *src, const Opnd &o, long c0, long m) {
   });
 }
 void copy_stream(void *dst, const void *src, size_t n);   // hostcopy.cpp: non-temporal stores
-static void par_memcpy(void *dst, const void *src, size_t bytes) {
+static void par_memcpy(void *dst, const void *src, size_t bytes, bool streaming = true) {
   host_parallel_for(bytes, (size_t)1 << 20, [&](size_t lo, size_t hi) {
-    copy_stream(static_cast<char *>(dst) + lo, static_cast<const char *>(src) + lo, hi - lo);
+    if (streaming) copy_stream(static_cast<char *>(dst) + lo, static_cast<const char *>(src) + lo, hi - lo);
+    else memcpy(static_cast<char *>(dst) + lo, static_cast<const char *>(src) + lo, hi - lo);
   });
 }
 
@@ -220,7 +221,7 @@ int Stager::in(int slot, int which, const Opnd &o, long c0, long m, const void *
   } else {
     void *bb = nullptr;
     NUK_TRY(bounce_buf(slot, which, &bb));
-    if (unit) par_memcpy(bb, chunk_lo(o, c0, m), bytes);   // address order
+    if (unit) par_memcpy(bb, chunk_lo(o, c0, m), bytes, opt(OPT_STAGE_NT) != 0);   // address order
     else gather(bb, o, c0, m);                             // logical order
     NUK_CUDA(cudaMemcpyAsync(dbuf, bb, bytes, cudaMemcpyHostToDevice, st));
     dirty[slot] = true;

@@ -49,30 +49,46 @@ namespace nuk {
 #define NUK_TRIG_MINB 4
 #endif
 #ifndef NUK_SINCOS64_UNROLL
-#define NUK_SINCOS64_UNROLL NUK_F64_UNROLL
+#define NUK_SINCOS64_UNROLL 4
 #endif
+// packs per thread / register caps from same-box A/B runs (profiles/ab_f64b_r02.txt, ab_f64c_r02.txt): atan 4 packs
+// uncapped 0.683 -> 0.718, tan 4 packs 0.540 -> 0.580, asin / acos 3 packs 0.745 -> 0.758 / 0.744 -> 0.770,
+// atan2 2 packs at 64 registers 0.829 -> 0.934 of the measured peak
 #ifndef NUK_ATAN64_UNROLL
-#define NUK_ATAN64_UNROLL NUK_F64_UNROLL
+#define NUK_ATAN64_UNROLL 4
 #endif
 #ifndef NUK_ATAN64_BATCH
 #define NUK_ATAN64_BATCH 0
 #endif
 #ifndef NUK_ATAN64_MINB
-#define NUK_ATAN64_MINB NUK_TRIG_MINB
+#define NUK_ATAN64_MINB 0
+#endif
+#ifndef NUK_TAN64_UNROLL
+#define NUK_TAN64_UNROLL 4
+#endif
+#ifndef NUK_ASIN64_UNROLL
+#define NUK_ASIN64_UNROLL 3
 #endif
 #ifndef NUK_ASIN64_MINB
 #define NUK_ASIN64_MINB 0
 #endif
 // cos capped at 32 registers: 74 -> 86 % (profiles/minblocks_sweep_r01.txt)
-NUK_F64_UNARY_FAST(SinD, sin_f64, 0, false, NUK_SINCOS64_UNROLL, 0) NUK_F64_UNARY_FAST(CosD, cos_f64, 8, false, NUK_SINCOS64_UNROLL, 0)
-NUK_F64_UNARY_FAST(TanD, tan_f64, 5, NUK_FAST_TRIG64, NUK_F64_UNROLL, 0)
-NUK_F64_UNARY_FAST(AsinD, asin_f64, NUK_ASIN64_MINB, NUK_FAST_INV64, NUK_F64_UNROLL, 0) NUK_F64_UNARY_FAST(AcosD, acos_f64, NUK_ASIN64_MINB, NUK_FAST_INV64, NUK_F64_UNROLL, 0)
+NUK_F64_UNARY_FAST(SinD, sin_f64, 0, false, NUK_SINCOS64_UNROLL, 0)   // 4 packs per thread: sin 0.811 -> 0.840, cos 0.863 -> 0.879 (profiles/ab_f64b_r02.txt)
+ NUK_F64_UNARY_FAST(CosD, cos_f64, 8, false, NUK_SINCOS64_UNROLL, 0)
+NUK_F64_UNARY_FAST(TanD, tan_f64, 5, NUK_FAST_TRIG64, NUK_TAN64_UNROLL, 0)
+NUK_F64_UNARY_FAST(AsinD, asin_f64, NUK_ASIN64_MINB, NUK_FAST_INV64, NUK_ASIN64_UNROLL, 0) NUK_F64_UNARY_FAST(AcosD, acos_f64, NUK_ASIN64_MINB, NUK_FAST_INV64, NUK_ASIN64_UNROLL, 0)
 NUK_F64_UNARY_FAST(AtanD, atan_f64, NUK_ATAN64_MINB, NUK_FAST_INV64, NUK_ATAN64_UNROLL, NUK_ATAN64_BATCH)
+#ifndef NUK_ATAN2_64_UNROLL
+#define NUK_ATAN2_64_UNROLL 2
+#endif
+#ifndef NUK_ATAN2_64_MINB
+#define NUK_ATAN2_64_MINB 4
+#endif
 struct Atan2D {
   using In = double; using Out = double;
   static constexpr int kArity = 2;
-  static constexpr int kMapUnroll = 1;
-  static constexpr int kMapMinBlocks = 5;
+  static constexpr int kMapUnroll = NUK_ATAN2_64_UNROLL;
+  static constexpr int kMapMinBlocks = NUK_ATAN2_64_MINB;
   static constexpr int kRowsUnroll = 1, kRowsMinBlocks = 5;
   static constexpr bool kHasFast = NUK_FAST_INV64;
   NUK_D double operator()(double a, double b) const { return nukmath::atan2_f64(a, b); }
