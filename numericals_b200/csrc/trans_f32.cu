@@ -100,6 +100,7 @@ NUK_F32_UNARY_FAST(AtanF, atan_f32, NUK_ATAN32_UNROLL, 0, NUK_FAST_ATAN32) NUK_F
     static constexpr int kMapMinBlocks = NUK_HYPINV32_MINB; \
     static constexpr bool kHasFast = (ON) == 1;         \
     static constexpr bool kWarpSplit = (ON) == 2;       \
+    static constexpr bool kCallFlaggedOnly = true;      /* a mixed warp: only the lanes outside the region run the logarithm path */ \
     NUK_D float operator()(float a) const { return nukmath::FN(a, tab); } \
     NUK_D float fast(float a, bool &slow) const { return nukmath::FN##_fast(a, tab, slow); } \
   };

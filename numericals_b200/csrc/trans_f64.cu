@@ -169,6 +169,7 @@ NUK_F64_TAB_UNARY(ExpD, exp_f64, TabExp, 6) NUK_F64_TAB_UNARY(LogD, log_f64, Tab
     static constexpr bool kWarpSplit = NUK_IHYP64_SPLIT == 2; \
     static constexpr bool kFastBatch = NUK_IHYP64_SPLIT == 3; \
     static constexpr bool kBatchCall = true;            \
+    static constexpr bool kCallFlaggedOnly = true;      \
     NUK_D double operator()(double a) const { return nukmath::FN(a, tab); } \
     NUK_D double fast(double a, bool &slow) const { return nukmath::FN##_fast(a, tab, slow); } \
   };

@@ -78,6 +78,28 @@ def test_unary(name, dt, nu, oracle):
     assert np.array_equal(np.isnan(got), np.isnan(truth)), name
 
 
+@pytest.mark.parametrize("name", ["asinh", "acosh", "sin", "atan"])
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_mixed_warps_of_the_vote_split(name, dt, nu):
+    """The per-warp vote (map.cuh:kWarpSplit) with flagged-lanes-only calls: SHUFFLED arguments, so that nearly every
+    warp holds elements inside AND outside the main path's region (asinh: |x| <= 1, acosh: (1, 3]; sin: |x| < 2^17)
+    next to specials -- device == host compile of the complete function, bit for bit, whatever the neighbours are;
+    and the same values in a different order give the same results (no dependence on the warp's other lanes)."""
+    rng = np.random.default_rng(77)
+    x = inputs(dt, rng)
+    if name == "acosh":
+        x = np.concatenate([x, (1 + rng.random(1 << 18) * 3).astype(dt), (1 + rng.random(1 << 16) * 1e-6).astype(dt)])
+    perm = rng.permutation(x.size)
+    xs = x[perm]
+    got = device_unary(nu, name, xs)
+    host = host_unary(name, xs)
+    same = (got.view(np.uint8).reshape(xs.size, -1) == host.view(np.uint8).reshape(xs.size, -1)).all(axis=1) | (np.isnan(got) & np.isnan(host))
+    assert same.all(), (name, dt, int((~same).sum()), xs[~same][:4])
+    back = device_unary(nu, name, x)
+    a, b = back[perm], got
+    assert ((a.view(np.uint8).reshape(xs.size, -1) == b.view(np.uint8).reshape(xs.size, -1)).all(axis=1) | (np.isnan(a) & np.isnan(b))).all()
+
+
 @pytest.mark.parametrize("name", ["exp", "sin", "log", "tanh", "cos"])
 def test_c2_functions_dense_bit_patterns(name, nu):
     """EVERY single-float in [2^-7, 8) and its negative (2 x 83.9M bit patterns): the device result

@@ -1,5 +1,5 @@
 #!/bin/bash
-# tools/ulp_report.sh -- regenerate profiles/ulp_report_r01.jsonl: EXHAUSTIVE (2^32 inputs) sweeps of
+# tools/ulp_report.sh -- regenerate profiles/ulp_report_r0N.jsonl (pass the path): EXHAUSTIVE (2^32 inputs) sweeps of
 # every single-float unary function, 4e7-sample sweeps of every double function, 4e8 / 1e8 samples of
 # the binary ones, against glibc (double / long double) and SLEEF u10.  ~40 min on 8 cores.
 set -e
