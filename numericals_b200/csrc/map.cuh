@@ -106,6 +106,14 @@ template <class F> struct FastBatch<F, std::void_t<decltype(F::kFastBatch)>> { s
 // kBatchCall: the re-do of a flagged element CALLS the complete function (one copy per kernel) instead of inlining it
 template <class F, class = void> struct BatchCall { static constexpr bool value = false; };
 template <class F> struct BatchCall<F, std::void_t<decltype(F::kBatchCall)>> { static constexpr bool value = F::kBatchCall; };
+// kRegionSplit: a functor whose function has a cheap closed region (asinh on |x| <= 1, acosh on (1, 3]: a polynomial
+// instead of the logarithm path) provides in_region(a) and region(a) next to the fast() / operator() pair of its
+// GENERAL path.  The thread tests its whole tile, the warp votes ONCE, and a warp whose 32 x UNROLL x E arguments are
+// all inside runs region() for them -- straight-line code, nothing else; any other warp runs the general pack-level
+// split unchanged, where fast() flags the in-region arguments too and the complete function (which branches to the
+// same polynomial) re-does them: an element's result never depends on the path its neighbours forced.
+template <class F, class = void> struct RegionSplit { static constexpr bool value = false; };
+template <class F> struct RegionSplit<F, std::void_t<decltype(F::kRegionSplit)>> { static constexpr bool value = F::kRegionSplit; };
 template <class F, class = void> struct CallFlaggedOnly { static constexpr bool value = false; };
 template <class F> struct CallFlaggedOnly<F, std::void_t<decltype(F::kCallFlaggedOnly)>> { static constexpr bool value = F::kCallFlaggedOnly; };
 template <class F> __device__ __noinline__ typename F::Out apply_called(F f, typename F::In a, typename F::In b) {
@@ -189,6 +197,24 @@ k_map_flat(size_t n, const typename F::In *x, const typename F::In *y, typename 
       for (int u = 0; u < UNROLL; ++u) b[u] = ld_stream(yp + base + (size_t)u * kThreads);
     }
     stage_tables(f);   // after the operand loads are in flight: the table copy hides under their latency
+    if constexpr (RegionSplit<F>::value) {
+      bool inside = true;
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) inside &= f.in_region(a[u].v[e]);
+      }
+      if (__all_sync(0xffffffffu, inside)) {
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+          POut r;
+#pragma unroll
+          for (int e = 0; e < E; ++e) r.v[e] = f.region(a[u].v[e]);
+          st_stream(op + base + (size_t)u * kThreads, r);
+        }
+        return;
+      }
+    }
     if constexpr (FastBatch<F>::value) {
       POut r[UNROLL];
       uint32_t flags = 0;

@@ -100,16 +100,30 @@ NUK_F32_UNARY_FAST(AtanF, atan_f32, NUK_ATAN32_UNROLL, 0, NUK_FAST_ATAN32) NUK_F
     static constexpr int kMapMinBlocks = NUK_HYPINV32_MINB; \
     static constexpr bool kHasFast = (ON) == 1;         \
     static constexpr bool kWarpSplit = (ON) == 2;       \
-    static constexpr bool kCallFlaggedOnly = true;      /* a mixed warp: only the lanes outside the region run the logarithm path */ \
     NUK_D float operator()(float a) const { return nukmath::FN(a, tab); } \
     NUK_D float fast(float a, bool &slow) const { return nukmath::FN##_fast(a, tab, slow); } \
   };
 // asinh on |x| <= 1 and acosh on (1, 3] are single-float polynomials (nukmath_f32.cuh:asinh_small_f32 / acosh_near_f32:
-// ~20 / ~28 instructions per element, HBM-bound); a warp holding anything else calls the complete double-table function
+// ~20 / ~31 instructions per element, HBM-bound) for a warp whose whole tile lies inside (map.cuh:kRegionSplit); every
+// other warp runs the double-table logarithm path as the pack-level split it was before the regions existed
 #ifndef NUK_ASINH32_UNROLL
-#define NUK_ASINH32_UNROLL 8
+#define NUK_ASINH32_UNROLL 4
 #endif
-NUK_F32_UNARY_TAB(AsinhF, asinh_f32, NUK_ASINH32_UNROLL, 2) NUK_F32_UNARY_TAB(AcoshF, acosh_f32, NUK_ASINH32_UNROLL, 2)
+#define NUK_F32_UNARY_REGION(Name, FN, POLY, INSIDE)    \
+  struct Name : TabPowF {                               \
+    using In = float; using Out = float;                \
+    static constexpr int kArity = 1;                    \
+    static constexpr int kMapUnroll = NUK_ASINH32_UNROLL; \
+    static constexpr int kMapMinBlocks = NUK_HYPINV32_MINB; \
+    static constexpr bool kHasFast = true;              \
+    static constexpr bool kRegionSplit = true;          \
+    NUK_D bool in_region(float a) const { return INSIDE; } \
+    NUK_D float region(float a) const { return nukmath::POLY(a); } \
+    NUK_D float operator()(float a) const { return nukmath::FN(a, tab); } \
+    NUK_D float fast(float a, bool &slow) const { return nukmath::FN##_general(a, tab, slow); } \
+  };
+NUK_F32_UNARY_REGION(AsinhF, asinh_f32, asinh_small_f32, fabsf(a) <= 1.0f)
+NUK_F32_UNARY_REGION(AcoshF, acosh_f32, acosh_near_f32, a > 1.0f && a <= 3.0f)
 NUK_F32_UNARY_TAB(AtanhF, atanh_f32, NUK_HYPINV32_UNROLL, 1)
 struct Atan2F {
   using In = float; using Out = float;

@@ -151,29 +151,26 @@ NUK_F64_TAB_UNARY(ExpD, exp_f64, TabExp, 6) NUK_F64_TAB_UNARY(LogD, log_f64, Tab
     NUK_D double operator()(double a) const { return nukmath::FN(a, tab); } \
     NUK_D double fast(double a, bool &slow) const { return nukmath::FN##_fast(a, tab, slow); } \
   };
-// asinh on |x| <= 1 and acosh on (1, 3] are polynomial main paths (nukmath_tab.cuh:asinh_small_f64 / acosh_near_f64);
-// the complete functions (logarithm path) are CALLED for a warp that holds anything else (map.cuh:kWarpSplit)
-#ifndef NUK_IHYP64_SPLIT
-#define NUK_IHYP64_SPLIT 2   // (profiles/ab_f64_r02.txt: asinh 1.05 with the vote, 0.83 with the batch) 1 pack split (complete function inlined per flagged element), 2 per-warp vote + call, 3 whole-tile batch + call (the 22 coefficients are fetched once per tile, not once per element)
-#endif
+// asinh on |x| <= 1 and acosh on (1, 3] are polynomials (nukmath_tab.cuh:asinh_small_f64 / acosh_near_f64) for a warp whose
+// whole tile lies inside (map.cuh:kRegionSplit); every other warp runs the logarithm path as the pack-level split it was
 #ifndef NUK_IHYP64_UNROLL
 #define NUK_IHYP64_UNROLL 4
 #endif
-#define NUK_F64_TAB_UNARY_REGION(Name, FN, Stage)       \
-  struct Name : Stage {                                 \
+#define NUK_F64_TAB_UNARY_REGION(Name, FN, POLY, INSIDE) \
+  struct Name : TabLog {                                \
     using In = double; using Out = double;              \
     static constexpr int kArity = 1;                    \
     static constexpr int kMapUnroll = NUK_IHYP64_UNROLL; \
-    static constexpr int kMapMinBlocks = 0;             \
-    static constexpr bool kHasFast = NUK_IHYP64_SPLIT == 1 || NUK_IHYP64_SPLIT == 3; \
-    static constexpr bool kWarpSplit = NUK_IHYP64_SPLIT == 2; \
-    static constexpr bool kFastBatch = NUK_IHYP64_SPLIT == 3; \
-    static constexpr bool kBatchCall = true;            \
-    static constexpr bool kCallFlaggedOnly = true;      \
+    static constexpr int kMapMinBlocks = NUK_IHYP_MINB; \
+    static constexpr bool kHasFast = true;              \
+    static constexpr bool kRegionSplit = true;          \
+    NUK_D bool in_region(double a) const { return INSIDE; } \
+    NUK_D double region(double a) const { return nukmath::POLY(a); } \
     NUK_D double operator()(double a) const { return nukmath::FN(a, tab); } \
-    NUK_D double fast(double a, bool &slow) const { return nukmath::FN##_fast(a, tab, slow); } \
+    NUK_D double fast(double a, bool &slow) const { return nukmath::FN##_general(a, tab, slow); } \
   };
-NUK_F64_TAB_UNARY_REGION(AsinhD, asinh_f64, TabLog) NUK_F64_TAB_UNARY_REGION(AcoshD, acosh_f64, TabLog)
+NUK_F64_TAB_UNARY_REGION(AsinhD, asinh_f64, asinh_small_f64, fabs(a) <= 1.0)
+NUK_F64_TAB_UNARY_REGION(AcoshD, acosh_f64, acosh_near_f64, a > 1.0 && a <= 3.0)
 NUK_F64_TAB_UNARY_FAST2(AtanhD, atanh_f64, TabLog, NUK_IHYP_MINB, NUK_FAST_IHYP64)
 // sinh / cosh: ~50-64 instructions per element and two per-lane indexed table reads each (the 32-entry table: 4
 // shared-memory wavefronts per read)

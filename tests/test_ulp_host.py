@@ -43,3 +43,16 @@ def test_binary_samples(fn, typ, sweep):
     r = json.loads(out.strip().splitlines()[-1])
     assert r["max_ulp"] < 1.0, r
     assert r["max_ulp_dist_vs_sleef_u10"] <= 1, r
+
+
+def test_f64_main_paths_equal_complete_functions(sweep):
+    """Every branch-free main path of the double functions (pack split, region split: asinh / acosh polynomial AND
+    logarithm paths) returns the complete function's bits wherever it does not raise `slow` -- so which path a tile
+    takes on the device (map.cuh:kRegionSplit votes per warp) can never change a result.  The exhaustive single-float
+    counterpart (`ulp_sweep all fast32`, all 2^32 inputs per function) is recorded in profiles/fast_vs_full_r02.jsonl."""
+    out = subprocess.check_output([sweep, "all", "fast64", "400000"]).decode()
+    rows = [json.loads(l) for l in out.strip().splitlines()]
+    assert len(rows) >= 13
+    for r in rows:
+        assert r["fast_differs_from_full"] == 0, r
+        assert r["flagged_slow"] < r["inputs"], r

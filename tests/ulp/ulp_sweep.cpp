@@ -156,11 +156,14 @@ struct Fast32 { const char *name; f32_fn full; f32_fast_fn fast; };
 static float asinh_f32_fast_h(float x, bool &s) { return nukmath::asinh_f32_fast(x, nukmath::TabRef{nukmath::kTabImageF}, s); }
 static float acosh_f32_fast_h(float x, bool &s) { return nukmath::acosh_f32_fast(x, nukmath::TabRef{nukmath::kTabImageF}, s); }
 static float atanh_f32_fast_h(float x, bool &s) { return nukmath::atanh_f32_fast(x, nukmath::TabRef{nukmath::kTabImageF}, s); }
+static float asinh_f32_general_h(float x, bool &s) { return nukmath::asinh_f32_general(x, nukmath::TabRef{nukmath::kTabImageF}, s); }
+static float acosh_f32_general_h(float x, bool &s) { return nukmath::acosh_f32_general(x, nukmath::TabRef{nukmath::kTabImageF}, s); }
 #endif
 static const Fast32 kFast32[] = {
 #ifdef NUK_HAVE_F64
   {"asinh", nukmath::asinh_f32, asinh_f32_fast_h}, {"acosh", nukmath::acosh_f32, acosh_f32_fast_h},
   {"atanh", nukmath::atanh_f32, atanh_f32_fast_h},
+  {"asinh_general", nukmath::asinh_f32, asinh_f32_general_h}, {"acosh_general", nukmath::acosh_f32, acosh_f32_general_h},
 #endif
   {"log", nukmath::log_f32, nukmath::log_f32_fast},   {"sin", nukmath::sin_f32, nukmath::sin_f32_fast},
   {"cos", nukmath::cos_f32, nukmath::cos_f32_fast},   {"tan", nukmath::tan_f32, nukmath::tan_f32_fast},

@@ -8,6 +8,7 @@ o=gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q > $o/gputest_r02.log 2>&1; echo pytest=$?
 python __graft_entry__.py smoke > $o/smoke_r02.log 2>&1; echo smoke=$?
 python tools/sweep.py --out $o/sweep_r02.jsonl > $o/sweep_r02.log 2>&1; echo sweep=$?
+python tools/sweep.py --cooldown 1 --only ^s,^d --out $o/sweep_r02_cooldown.jsonl > $o/sweep_r02_cooldown.log 2>&1; echo sweepcool=$?
 python tools/time_regions.py > $o/time_regions_r02.txt 2>&1; echo regions=$?
 python bench.py --impl reference --steps 3 --warmup 1 > $o/bench_ref_r02_n1.json 2> $o/bench_ref_r02.err; echo ref=$?
 python bench.py > $o/bench_r02_n1.json 2> $o/bench_r02.err; echo bench=$?

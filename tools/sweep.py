@@ -32,6 +32,10 @@ def main():
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--out", default=None)
     ap.add_argument("--only", default=None, help="comma-separated substrings of the symbol name (dexp,spow); ^d = prefix")
+    ap.add_argument("--cooldown", type=float, default=0.0,
+                    help="idle seconds before each symbol: the default sweep runs ~150 kernels back to back and the FP64-heavy "
+                         "maps then sit under the board's power cap (SM clock 1965 -> 1500-1900 MHz, profiles/clockwatch_r01.txt); "
+                         "with a pause each symbol is timed like a kernel launched on its own")
     args = ap.parse_args()
     nu.require_device(0)
     lib = _lib.lib()
@@ -66,6 +70,9 @@ def main():
             nu.copy(t.broadcast_to((n // m, m)), out=view.reshape(n // m, m))
 
     def time_call(fn, call_args):
+        if args.cooldown > 0:
+            import time
+            time.sleep(args.cooldown)
         fn(*call_args)
         lib.nuk_stream_sync(st)
         best = None
@@ -85,6 +92,8 @@ def main():
         row = {"symbol": "BMAS_" + sym, "kind": kind, "n": n, "ms": round(ms, 5), "gelem_s": round(n / (ms / 1e3) / 1e9, 2),
                "algorithmic_bytes_per_elem": bytes_per_elem, "hbm_gbs": round(gbs, 1),
                "frac_of_measured_peak": round(gbs / peak, 4), "frac_of_8tbs": round(gbs / 8000.0, 4)}
+        if args.cooldown > 0:
+            row["cooldown_s"] = args.cooldown
         if sync_included:
             row["note"] = "returns by value: includes a D2H of the scalar and a stream sync"
         rows.append(row)
