@@ -7,7 +7,10 @@
 //                independent 128-bit requests per operand per thread in flight), streaming stores.
 //                Functor traits: kMapUnroll, kMapMinBlocks (register cap), kSmemBytes + stage() (lookup
 //                tables copied into shared memory once per CTA, after the operand loads are issued),
-//                kHasFast + fast() (branch-free main path for the whole pack, flagged elements re-done).
+//                kHasFast + fast() (branch-free main path for the whole pack, flagged elements re-done),
+//                kWarpSplit (the same pair split by a per-warp vote, rare path called), kRegionSplit + in_region()
+//                + region() (one vote per tile: a warp entirely inside a cheap closed region runs only that),
+//                kFastBatch / kBatchCall (whole-tile batch: an A/B option, no functor uses it by default).
 //   k_map_rows : inner axis contiguous for OUT, inputs contiguous or broadcast (stride 0)
 //                along it; outer axes arbitrary.  A CTA owns a column tile x a group of
 //                consecutive rows; an operand that does not vary with the row (row-vector
