@@ -20,6 +20,7 @@
 #include <atomic>
 #include <cfloat>
 #include <limits>
+#include <type_traits>
 #include "dispatch.cuh"
 #include "ops.cuh"
 #include "comm.cuh"
@@ -687,7 +688,13 @@ template <class R> static int run_full(const ReduceProblem &p, typename R::Acc i
   const T *first = ((p.red == NUK_HMAX || p.red == NUK_HMIN) && !(p.flags & NUK_REDUCE_NO_SEED) && n > 0) ? x : nullptr;
   if (contig && aligned_to(x, 16)) {
     const size_t tiles = n / E / ((size_t)kThreads * UNROLL) + 1;
-    grid = grid_for(tiles, (int)opt(OPT_REDUCE_GRID_MULT));
+    // 8-bit extrema: a quarter of the CTAs (4 per SM instead of 16).  Their fold is ALU work (two extracts and two 16x2
+    // maxima per word, issued at half rate) and a 2^28-element array is only ~7 tiles per CTA at 16 per SM, so the
+    // per-CTA epilogue (unpack, block tree, ticket) weighs in: i8hmax 0.868 -> 0.917, u8hmax 0.856 -> 0.930 of the
+    // measured peak, the sums and the wider extrema are best at 16 (profiles/ab_reduce_grid_r02.txt)
+    constexpr bool kByteExtremum = sizeof(T) == 1 && WordRed<R>::ok && !std::is_same<R, SumR<T>>::value;
+    const int mult = (int)opt(OPT_REDUCE_GRID_MULT);
+    grid = grid_for(tiles, kByteExtremum ? (mult + 3) / 4 : mult);
     NUK_TRY(partial_space(sizeof(A) * (size_t)grid, &scratch_ptr));
     k_reduce_flat<R, UNROLL><<<grid, kThreads, 0, p.stream>>>(n, x, static_cast<A *>(scratch_ptr), init, ticket, o1, o2,
                                                               first);
