@@ -419,7 +419,9 @@ k_map_flat2(size_t n, int64_t ncols, const typename F::In *x, const typename F::
 #pragma unroll
       for (int w = 0; w < 4; ++w) wr[w] = Word4<F>::op(wa[w], wb[w]);
       memcpy(&r, wr, 16);
-    } else if constexpr (HasFast<F>::value) {
+    // (a region functor's fast() is its GENERAL path and flags in-region arguments: without the tile vote of k_map_flat
+    // the complete function, which branches to the region itself, is the better per-element form -- here and in k_map_rows)
+    } else if constexpr (HasFast<F>::value && !RegionSplit<F>::value) {
       bool slow[E], any = false;
 #pragma unroll
       for (int e = 0; e < E; ++e) {
@@ -582,7 +584,7 @@ k_map_rows(RowsDesc d, const typename F::In *x, const typename F::In *y, typenam
       const int64_t c = c0 + (int64_t)u * kThreads * E;
       if (full[u]) {
         POut rr;
-        if constexpr (HasFast<F>::value && NUK_ROWS_FAST) {
+        if constexpr (HasFast<F>::value && !RegionSplit<F>::value && NUK_ROWS_FAST) {
           In av[E], bv[E];
           bool slow[E], any = false;
 #pragma unroll
