@@ -117,8 +117,6 @@ template <class F> struct BatchCall<F, std::void_t<decltype(F::kBatchCall)>> { s
 // same polynomial) re-does them: an element's result never depends on the path its neighbours forced.
 template <class F, class = void> struct RegionSplit { static constexpr bool value = false; };
 template <class F> struct RegionSplit<F, std::void_t<decltype(F::kRegionSplit)>> { static constexpr bool value = F::kRegionSplit; };
-template <class F, class = void> struct CallFlaggedOnly { static constexpr bool value = false; };
-template <class F> struct CallFlaggedOnly<F, std::void_t<decltype(F::kCallFlaggedOnly)>> { static constexpr bool value = F::kCallFlaggedOnly; };
 template <class F> __device__ __noinline__ typename F::Out apply_called(F f, typename F::In a, typename F::In b) {
   if constexpr (F::kArity == 2) return f(a, b);
   else return f(a);
@@ -273,13 +271,9 @@ k_map_flat(size_t n, const typename F::In *x, const typename F::In *y, typename 
         for (int e = 0; e < E; ++e) {
           bool slow = false;
           r.v[e] = apply_fast(f, a[u].v[e], F::kArity == 2 ? b[u].v[e] : In(), slow);
-          // kCallFlaggedOnly: only the flagged lanes take the call: fast() and the complete function agree bit for bit wherever fast() did
-          // not raise the flag (tests/ulp/ulp_sweep.cpp fast32, all 2^32 inputs), so the others keep what they have
-          // and a complete function with regions of its own (asinh, acosh) does not run every region for a mixed warp
-          // (kCallFlaggedOnly; the inner test puts a BSSY / BSYNC pair on the hot path, so it is opt-in: tanh f32 43 -> 46)
-          if (__any_sync(0xffffffffu, slow)) {
-            if (!CallFlaggedOnly<F>::value || slow) r.v[e] = apply_called(f, a[u].v[e], F::kArity == 2 ? b[u].v[e] : In());
-          }
+          // every lane of a flagged warp takes the call (restricting it to the flagged lanes puts a BSSY / BSYNC pair on
+          // the hot path: tanh f32 43 -> 46 instructions per element; the complete function returns fast()'s bits there)
+          if (__any_sync(0xffffffffu, slow)) r.v[e] = apply_called(f, a[u].v[e], F::kArity == 2 ? b[u].v[e] : In());
         }
 #endif
       } else if constexpr (HasFast<F>::value) {

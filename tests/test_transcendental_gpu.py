@@ -81,10 +81,11 @@ def test_unary(name, dt, nu, oracle):
 @pytest.mark.parametrize("name", ["asinh", "acosh", "sin", "atan"])
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 def test_mixed_warps_of_the_vote_split(name, dt, nu):
-    """The per-warp vote (map.cuh:kWarpSplit) with flagged-lanes-only calls: SHUFFLED arguments, so that nearly every
-    warp holds elements inside AND outside the main path's region (asinh: |x| <= 1, acosh: (1, 3]; sin: |x| < 2^17)
-    next to specials -- device == host compile of the complete function, bit for bit, whatever the neighbours are;
-    and the same values in a different order give the same results (no dependence on the warp's other lanes)."""
+    """The per-warp splits (map.cuh:kWarpSplit per element, kRegionSplit per tile): SHUFFLED arguments, so that nearly
+    every warp holds elements inside AND outside the main path's region (asinh: |x| <= 1, acosh: (1, 3]; sin:
+    |x| < 2^17) next to specials -- device == host compile of the complete function, bit for bit, whatever the
+    neighbours are; and the same values in a different order give the same results (no dependence on the warp's
+    other lanes)."""
     rng = np.random.default_rng(77)
     x = inputs(dt, rng)
     if name == "acosh":
