@@ -73,8 +73,17 @@ namespace nuk {
 #define NUK_ASIN64_MINB 0
 #endif
 // cos capped at 32 registers: 74 -> 86 % (profiles/minblocks_sweep_r01.txt)
-NUK_F64_UNARY_FAST(SinD, sin_f64, 0, false, NUK_SINCOS64_UNROLL, 0)   // 4 packs per thread: sin 0.811 -> 0.840, cos 0.863 -> 0.879 (profiles/ab_f64b_r02.txt)
- NUK_F64_UNARY_FAST(CosD, cos_f64, 8, false, NUK_SINCOS64_UNROLL, 0)
+#ifndef NUK_SINCOS64_FAST
+#define NUK_SINCOS64_FAST false   // the pack-level split is still slower at 4 packs per thread (profiles/ab_sincos64_r02.txt: sin 0.840 -> 0.831, cos 0.879 -> 0.817; register caps of 5 / 6 change nothing or lose)
+#endif
+#ifndef NUK_SIN64_MINB
+#define NUK_SIN64_MINB 0
+#endif
+#ifndef NUK_COS64_MINB
+#define NUK_COS64_MINB 8
+#endif
+NUK_F64_UNARY_FAST(SinD, sin_f64, NUK_SIN64_MINB, NUK_SINCOS64_FAST, NUK_SINCOS64_UNROLL, 0)   // 4 packs per thread: sin 0.811 -> 0.840, cos 0.863 -> 0.879 (profiles/ab_f64b_r02.txt)
+ NUK_F64_UNARY_FAST(CosD, cos_f64, NUK_COS64_MINB, NUK_SINCOS64_FAST, NUK_SINCOS64_UNROLL, 0)
 NUK_F64_UNARY_FAST(TanD, tan_f64, 5, NUK_FAST_TRIG64, NUK_TAN64_UNROLL, 0)
 NUK_F64_UNARY_FAST(AsinD, asin_f64, NUK_ASIN64_MINB, NUK_FAST_INV64, NUK_ASIN64_UNROLL, 0) NUK_F64_UNARY_FAST(AcosD, acos_f64, NUK_ASIN64_MINB, NUK_FAST_INV64, NUK_ASIN64_UNROLL, 0)
 NUK_F64_UNARY_FAST(AtanD, atan_f64, NUK_ATAN64_MINB, NUK_FAST_INV64, NUK_ATAN64_UNROLL, NUK_ATAN64_BATCH)
