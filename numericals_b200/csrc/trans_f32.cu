@@ -136,7 +136,7 @@ struct Atan2F {
   NUK_D float fast(float a, float b, bool &slow) const { return nukmath::atan2_f32_fast(a, b, slow); }
 };
 #ifndef NUK_POWF_MINB
-#define NUK_POWF_MINB 5    // 48 registers: 0.59 ms per 2^28 (83 %); uncapped (88 registers, 2 CTAs/SM) 0.89 ms
+#define NUK_POWF_MINB 5    // 48 registers: 0.59 ms per 2^28 (83 %); uncapped (88 registers, 2 CTAs/SM) 0.89 ms.  Re-checked after the table re-layout (profiles/ab_powf_r02.txt): 0.869 of the measured peak; caps of 4 / 6 0.794 / 0.743, 4 packs 0.738, 1 pack 0.625
 #endif
 #ifndef NUK_POWF_UNROLL
 #define NUK_POWF_UNROLL 2
