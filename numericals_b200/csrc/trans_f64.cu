@@ -66,6 +66,9 @@ namespace nuk {
 #ifndef NUK_TAN64_UNROLL
 #define NUK_TAN64_UNROLL 4
 #endif
+#ifndef NUK_TAN64_MINB
+#define NUK_TAN64_MINB 5   // profiles/ab_tan64_r02.txt: 0.669 of the measured peak; caps of 3 / 4 / 6 / none 0.676 / 0.664 / 0.610 / 0.658
+#endif
 #ifndef NUK_ASIN64_UNROLL
 #define NUK_ASIN64_UNROLL 3
 #endif
@@ -84,7 +87,7 @@ namespace nuk {
 #endif
 NUK_F64_UNARY_FAST(SinD, sin_f64, NUK_SIN64_MINB, NUK_SINCOS64_FAST, NUK_SINCOS64_UNROLL, 0)   // 4 packs per thread: sin 0.811 -> 0.840, cos 0.863 -> 0.879 (profiles/ab_f64b_r02.txt)
  NUK_F64_UNARY_FAST(CosD, cos_f64, NUK_COS64_MINB, NUK_SINCOS64_FAST, NUK_SINCOS64_UNROLL, 0)
-NUK_F64_UNARY_FAST(TanD, tan_f64, 5, NUK_FAST_TRIG64, NUK_TAN64_UNROLL, 0)
+NUK_F64_UNARY_FAST(TanD, tan_f64, NUK_TAN64_MINB, NUK_FAST_TRIG64, NUK_TAN64_UNROLL, 0)
 NUK_F64_UNARY_FAST(AsinD, asin_f64, NUK_ASIN64_MINB, NUK_FAST_INV64, NUK_ASIN64_UNROLL, 0) NUK_F64_UNARY_FAST(AcosD, acos_f64, NUK_ASIN64_MINB, NUK_FAST_INV64, NUK_ASIN64_UNROLL, 0)
 NUK_F64_UNARY_FAST(AtanD, atan_f64, NUK_ATAN64_MINB, NUK_FAST_INV64, NUK_ATAN64_UNROLL, NUK_ATAN64_BATCH)
 #ifndef NUK_ATAN2_64_UNROLL
