@@ -73,7 +73,10 @@ namespace nuk {
 #define NUK_ASIN64_UNROLL 3
 #endif
 #ifndef NUK_ASIN64_MINB
-#define NUK_ASIN64_MINB 0
+#define NUK_ASIN64_MINB 8   // 32 registers: asin 0.834 -> 0.871 of the measured peak; acos is best uncapped (0.868; 0.839 at 8) -- profiles/ab_asin64_r02.txt
+#endif
+#ifndef NUK_ACOS64_MINB
+#define NUK_ACOS64_MINB 0
 #endif
 // cos capped at 32 registers: 74 -> 86 % (profiles/minblocks_sweep_r01.txt)
 #ifndef NUK_SINCOS64_FAST
@@ -88,7 +91,7 @@ namespace nuk {
 NUK_F64_UNARY_FAST(SinD, sin_f64, NUK_SIN64_MINB, NUK_SINCOS64_FAST, NUK_SINCOS64_UNROLL, 0)   // 4 packs per thread: sin 0.811 -> 0.840, cos 0.863 -> 0.879 (profiles/ab_f64b_r02.txt)
  NUK_F64_UNARY_FAST(CosD, cos_f64, NUK_COS64_MINB, NUK_SINCOS64_FAST, NUK_SINCOS64_UNROLL, 0)
 NUK_F64_UNARY_FAST(TanD, tan_f64, NUK_TAN64_MINB, NUK_FAST_TRIG64, NUK_TAN64_UNROLL, 0)
-NUK_F64_UNARY_FAST(AsinD, asin_f64, NUK_ASIN64_MINB, NUK_FAST_INV64, NUK_ASIN64_UNROLL, 0) NUK_F64_UNARY_FAST(AcosD, acos_f64, NUK_ASIN64_MINB, NUK_FAST_INV64, NUK_ASIN64_UNROLL, 0)
+NUK_F64_UNARY_FAST(AsinD, asin_f64, NUK_ASIN64_MINB, NUK_FAST_INV64, NUK_ASIN64_UNROLL, 0) NUK_F64_UNARY_FAST(AcosD, acos_f64, NUK_ACOS64_MINB, NUK_FAST_INV64, NUK_ASIN64_UNROLL, 0)
 NUK_F64_UNARY_FAST(AtanD, atan_f64, NUK_ATAN64_MINB, NUK_FAST_INV64, NUK_ATAN64_UNROLL, NUK_ATAN64_BATCH)
 #ifndef NUK_ATAN2_64_UNROLL
 #define NUK_ATAN2_64_UNROLL 2
