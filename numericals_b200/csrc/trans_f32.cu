@@ -85,7 +85,7 @@ NUK_F32_UNARY_U(ExpF, exp_f32, 2)   // 5.9 TB/s with 2 packs per thread vs 5.2 w
 #endif
 NUK_F32_UNARY_FAST(TanF, tan_f32, NUK_TAN32_UNROLL, 0, NUK_FAST_TRIG32) NUK_F32_UNARY_FAST(AsinF, asin_f32, NUK_ATAN32_UNROLL, 0, NUK_FAST_ATAN32) NUK_F32_UNARY_FAST(AcosF, acos_f32, NUK_ATAN32_UNROLL, 0, NUK_FAST_ATAN32)
 NUK_F32_UNARY_FAST(AtanF, atan_f32, NUK_ATAN32_UNROLL, 0, NUK_FAST_ATAN32) NUK_F32_UNARY_FAST(SinhF, sinh_f32, NUK_F32_UNROLL, 0, NUK_FAST_HYP32) NUK_F32_UNARY_FAST(CoshF, cosh_f32, NUK_F32_UNROLL, 0, NUK_FAST_HYP32)
-// asinh / acosh / atanh: double arithmetic on the 640 bytes of single-float pow tables (nukmath_tab.cuh)
+// atanh, and asinh / acosh outside their polynomial regions: double arithmetic on the 768 bytes of single-float pow tables (nukmath_tab.cuh)
 #ifndef NUK_HYPINV32_MINB
 #define NUK_HYPINV32_MINB 0
 #endif
@@ -141,7 +141,7 @@ struct Atan2F {
 #ifndef NUK_POWF_UNROLL
 #define NUK_POWF_UNROLL 2
 #endif
-struct PowF : TabPowF {   // 640 bytes of tables in shared memory (nukmath_tab.cuh:pow_f32)
+struct PowF : TabPowF {   // 768 bytes of tables in shared memory (nukmath_tab.cuh:pow_f32)
   using In = float; using Out = float;
   static constexpr int kArity = 2;
   static constexpr int kMapUnroll = NUK_POWF_UNROLL;
